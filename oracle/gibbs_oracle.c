@@ -40,7 +40,8 @@
  *                   else Hormann BTRS; flip back if pp>0.5
  *   fp reductions: PE = fma chain over k; corrP = fma chain over i; corrE = 128-column segment
  *                  fma chains, segments added in ascending order (per shard, shards ascending);
- *                  loglik = per-column sequential sums, then stride-halving tree over columns.
+ *                  loglik = per-column sums in 32-row chunks (chunks added in order), then a
+ *                  stride-halving tree over the zero-padded column array.
  */
 #include <math.h>
 #include <stdint.h>
@@ -48,6 +49,7 @@
 #include <string.h>
 
 #define ORACLE_SEG 128
+#define ORACLE_LLCHUNK 32
 #define BINV_MAX 10.0
 #define TINY 1e-160
 #define AUX_BLOCK 0xFFFFFFFFu
@@ -539,13 +541,18 @@ double oracle_loglik(int I, int J, int K, const double *M, const double *W, cons
     double *col = calloc(n2, sizeof(double)), *lgm = calloc(n2, sizeof(double));
     for (int j = 0; j < J; j++) {
         double a = 0.0, b = 0.0;
-        for (int i = 0; i < I; i++) {
-            double pe = 0.0;
-            for (int k = 0; k < K; k++) pe = fma(P[i + (size_t)I * k], E[k + (size_t)K * j], pe);
-            double lam = pe * W[i + (size_t)I * j];
-            double m = (double)(int)M[i + (size_t)I * j];
-            a = a + (m * oracle_log(lam) - lam);
-            b = b + oracle_lgamma(m + 1.0);
+        for (int c0 = 0; c0 < I; c0 += ORACLE_LLCHUNK) {            /* 32-row chunks, added in order */
+            int c1 = c0 + ORACLE_LLCHUNK; if (c1 > I) c1 = I;
+            double ac = 0.0, bc = 0.0;
+            for (int i = c0; i < c1; i++) {
+                double pe = 0.0;
+                for (int k = 0; k < K; k++) pe = fma(P[i + (size_t)I * k], E[k + (size_t)K * j], pe);
+                double lam = pe * W[i + (size_t)I * j];
+                double m = (double)(int)M[i + (size_t)I * j];
+                ac = ac + (m * oracle_log(lam) - lam);
+                bc = bc + oracle_lgamma(m + 1.0);
+            }
+            a = a + ac; b = b + bc;
         }
         col[j] = a; lgm[j] = b;
     }

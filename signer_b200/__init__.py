@@ -1,0 +1,8 @@
+"""signer_b200 -- B200 (sm_100a) implementation of signeR's empirical-Bayes Poisson-NMF Gibbs
+sampler behind the reference's own boundary.  The CUDA library (libsigner_gibbs.so, C ABI in
+include/signer_gibbs.h) is the product; this package is the host-side mirror of the reference's
+R interface for that one path.  No CPU fallback exists."""
+from .gibbs import Chain, GibbsSamplerCpp, SampleList, set_seed   # noqa: F401
+from ._lib import SignerError                                     # noqa: F401
+
+__all__ = ["GibbsSamplerCpp", "Chain", "SampleList", "SignerError", "set_seed"]

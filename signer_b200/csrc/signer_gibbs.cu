@@ -1,0 +1,754 @@
+// signer_gibbs.cu -- host side of libsigner_gibbs.so: device-resident chains, the sweep scheduler
+// and the C ABI declared in include/signer_gibbs.h.
+//
+// Replaces the driver GibbsSamplerCpp (src/gibbs_2.cpp:253-424): flag logic (:265-267), the
+// random scan (:303-318), sample storage (:320-334) and the returned list (:406-423).
+// There is no CPU path in this file: every entry point that computes launches CUDA kernels.
+#include "../../include/signer_gibbs.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace sg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? SIGNER_ERR_NOMEM : SIGNER_ERR_CUDA,         \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+    } while (0)
+
+#define ST(call)                                  \
+    do {                                          \
+        int s_ = (call);                          \
+        if (s_ != SIGNER_OK) return s_;           \
+    } while (0)
+
+constexpr size_t kRingBytes = size_t(3) << 30;   // per ring set (two sets)
+
+// The data of one cohort on one device, shared by every chain on that device.
+struct DeviceData {
+    int device = 0, I = 0, J = 0, Jp = 0, n2 = 0;
+    int *M = nullptr;          // [I][Jp]
+    double *W = nullptr;       // [I][Jp]
+    double *lgm = nullptr;     // sum lgamma(M+1), one double
+    ~DeviceData()
+    {
+        cudaSetDevice(device);
+        cudaFree(M); cudaFree(W); cudaFree(lgm);
+    }
+};
+
+int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out)
+{
+    if (I <= 0 || J <= 0 || !M || !W) return fail(SIGNER_ERR_ARG, "problem: I, J must be positive and M, W non-null");
+    if ((long long)I * J >= (1LL << 31)) return fail(SIGNER_ERR_ARG, "problem: I*J must be below 2^31");
+    CU(cudaSetDevice(device));
+    auto d = std::make_shared<DeviceData>();
+    d->device = device; d->I = I; d->J = J; d->Jp = (J + 31) / 32 * 32;
+    d->n2 = 1; while (d->n2 < J) d->n2 <<= 1;
+    const size_t n = (size_t)I * d->Jp;
+    std::vector<int> m(n, 0);
+    std::vector<double> w(n, 0.0);
+    for (int j = 0; j < J; ++j)
+        for (int i = 0; i < I; ++i) {
+            const double mv = M[(size_t)i + (size_t)I * j], wv = W[(size_t)i + (size_t)I * j];
+            if (!(mv >= 0.0) || !(mv <= 2147483647.0)) return fail(SIGNER_ERR_NONFINITE, "M has a negative, non-finite or too large entry");
+            if (!(wv >= 0.0) || !(wv <= 1.7976931348623157e308)) return fail(SIGNER_ERR_NONFINITE, "W has a negative or non-finite entry");
+            m[(size_t)i * d->Jp + j] = (int)mv;          // int size (src/gibbs_2.cpp:31)
+            w[(size_t)i * d->Jp + j] = wv;
+        }
+    CU(cudaMalloc(&d->M, n * sizeof(int)));
+    CU(cudaMalloc(&d->W, n * sizeof(double)));
+    CU(cudaMalloc(&d->lgm, sizeof(double)));
+    CU(cudaMemcpy(d->M, m.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->W, w.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    // constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180)
+    double *col = nullptr;
+    CU(cudaMalloc(&col, (size_t)d->n2 * sizeof(double)));
+    CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
+    LLParams lp{I, J, d->Jp, 1, d->M, d->W, nullptr, nullptr, col, 1};
+    const int nchunk = (I + kLLChunk - 1) / kLLChunk;
+    const size_t smem = sizeof(double) * (size_t)(33 + nchunk * 32);
+    loglik_cols<<<(J + 31) / 32, 128, smem>>>(lp);
+    tree_sum<<<1, 1024>>>(col, d->n2, nullptr, d->lgm);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(col));
+    out = d;
+    return SIGNER_OK;
+}
+
+struct Ring {
+    double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr;
+    cudaEvent_t filled = nullptr, copied = nullptr;
+};
+
+} // namespace
+
+struct signer_chain {
+    std::shared_ptr<DeviceData> data;
+    int device = 0, I = 0, J = 0, Jp = 0, K = 0;
+    size_t nP = 0, nE = 0;
+    double *P = nullptr, *E = nullptr, *Ap = nullptr, *Bp = nullptr, *Ae = nullptr, *Be = nullptr;
+    int *Zin[2] = {nullptr, nullptr}, *Znj[2] = {nullptr, nullptr};
+    int zcur = 0;
+    double *corrE_part = nullptr;
+    int n_seg = 0;
+    double *col = nullptr, *ll_ring = nullptr;
+    int ll_cap = 0;
+    double *Zcube = nullptr;
+    double *stats = nullptr;
+    unsigned long long *tile_counter = nullptr;
+    unsigned long long z_launches = 0;
+    int z_grid = 0, n_rb = 0, n_tiles = 0;
+    int kg_per_split = 2, ksplit = 1;
+    Hyper h{};
+    Key key{};
+    uint32_t sweep0 = 0;
+    int64_t sweeps_done = 0;
+    int Pfixed = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    Ring ring[2];
+    int ring_cap = 0, ring_keep = 0;
+    int last_eval = 0;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];
+
+    ~signer_chain()
+    {
+        cudaSetDevice(device);
+        if (own_stream) cudaStreamSynchronize(own_stream);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, col, ll_ring, Zcube, stats}) cudaFree(p);
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(Zin[b]); cudaFree(Znj[b]);
+            free_ring(ring[b]);
+        }
+        cudaFree(tile_counter);
+        for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+    static void free_ring(Ring &r)
+    {
+        for (double *p : {r.Ps, r.Es, r.Aps, r.Aes, r.Bps, r.Bes}) cudaFree(p);
+        if (r.filled) cudaEventDestroy(r.filled);
+        if (r.copied) cudaEventDestroy(r.copied);
+        r = Ring{};
+    }
+};
+
+namespace {
+
+struct ProfScope {
+    signer_chain *c; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(signer_chain *c_, int cls_) : c(c_), cls(cls_)
+    {
+        if (!c->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope()
+    {
+        if (!c->profiling) return;
+        cudaEventRecord(b, c->stream);
+        c->ev[cls].emplace_back(a, b);
+    }
+};
+
+void host_perm(uint64_t seed, uint32_t sweep, int order[7])
+{
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const U4 a = philox4x32_10(0, 0, kStPerm, sweep, k0, k1), b = philox4x32_10(1, 0, kStPerm, sweep, k0, k1);
+    const uint32_t w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+    for (int i = 0; i < 7; ++i) order[i] = i + 1;
+    for (int idx = 6; idx >= 1; --idx) {
+        const uint32_t j = (uint32_t)(((uint64_t)w[6 - idx] * (uint64_t)(idx + 1)) >> 32);
+        std::swap(order[idx], order[j]);
+    }
+}
+
+int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
+{
+    const int tgt = c->zcur ^ 1;
+    ZParams p{};
+    p.I = c->I; p.J = c->J; p.Jp = c->Jp; p.K = c->K;
+    p.M = c->data->M; p.P = c->P; p.E = c->E;
+    p.Zin = c->Zin[tgt]; p.Znj = c->Znj[tgt];
+    p.Zin_next = c->Zin[c->zcur]; p.Znj_next = c->Znj[c->zcur];
+    p.Zcube = zcube;
+    p.tile_counter = c->tile_counter;
+    p.tile_base = c->z_launches * (unsigned long long)(c->n_tiles + c->z_grid);
+    p.n_rb = c->n_rb; p.n_tiles = c->n_tiles;
+    p.key = c->key; p.sweep = sweep; p.stream = stream_id;
+    if (zcube) CU(cudaMemsetAsync(zcube, 0, sizeof(double) * (size_t)c->I * c->J * c->K, c->stream));
+    {
+        ProfScope ps(c, 0);
+        z_alloc_fused<<<c->z_grid, kZThreads, z_smem_bytes(c->K), c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    c->z_launches++;
+    c->zcur = tgt;
+    return SIGNER_OK;
+}
+
+int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double *Aps, double *Bps)
+{
+    PParams p{};
+    p.IK = (int)c->nP; p.P = c->P; p.Ap = c->Ap; p.Bp = c->Bp;
+    p.Zin = c->Zin[c->zcur]; p.corrE_part = c->corrE_part; p.n_seg = c->n_seg; p.n_shards = 1;
+    p.Ps_slot = Ps; p.Aps_slot = Aps; p.Bps_slot = Bps;
+    p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
+    {
+        ProfScope ps(c, 1);
+        p_family<<<(p.IK + 127) / 128, 128, 0, c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return SIGNER_OK;
+}
+
+int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, double *Es, double *Aes, double *Bes)
+{
+    EParams p{};
+    p.I = c->I; p.J = c->J; p.Jp = c->Jp; p.K = c->K;
+    p.W = c->data->W; p.P = c->P; p.E = c->E; p.Ae = c->Ae; p.Be = c->Be;
+    p.Znj = c->Znj[c->zcur]; p.corrE_part = c->corrE_part;
+    p.kg_per_split = c->kg_per_split; p.do_corrE = do_corrE;
+    p.Es_slot = Es; p.Aes_slot = Aes; p.Bes_slot = Bes;
+    p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
+    {
+        ProfScope ps(c, 2);
+        e_family<<<dim3(c->n_seg, c->ksplit), kEThreads, e_smem_bytes(c->kg_per_split), c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return SIGNER_OK;
+}
+
+int launch_loglik(signer_chain *c, double *out)
+{
+    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->M, c->data->W, c->P, c->E, c->col, 0};
+    const int nchunk = (c->I + kLLChunk - 1) / kLLChunk;
+    const size_t smem = sizeof(double) * (size_t)(c->K * 33 + nchunk * 32);
+    {
+        ProfScope ps(c, 3);
+        loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
+        tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out);
+    }
+    CU(cudaGetLastError());
+    return SIGNER_OK;
+}
+
+struct Slots { double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr; };
+
+// One sweep: the seven steps of `order` (0 = skip) regrouped into at most three launches.
+int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slots *slots, double *zcube)
+{
+    Ops pops{0, 0u}, eops{0, 0u};
+    int pos1 = -1, posP = -1, posE = -1;
+    bool has2 = false, has3 = false;
+    for (int f = 0; f < 7; ++f) {
+        const int s = order[f];
+        if (s == 1) { if (pos1 < 0) pos1 = f; }
+        else if (s == 2 || s == 4 || s == 6) {
+            if (c->Pfixed) continue;                    // guards of src/gibbs_2.cpp:311,313,315
+            if (pops.n < 3) pops.push(s);
+            if (s == 2) { posP = f; has2 = true; } else if (!has2 && posP < 0) posP = f;
+        } else if (s == 3 || s == 5 || s == 7) {
+            if (eops.n < 3) eops.push(s);
+            if (s == 3) { posE = f; has3 = true; } else if (!has3 && posE < 0) posE = f;
+        }
+    }
+    struct Item { int pos, kind; } items[3];
+    int n = 0;
+    if (pos1 >= 0) items[n++] = {pos1, 1};
+    if (pops.n) items[n++] = {posP, 2};
+    if (eops.n) items[n++] = {posE, 3};
+    std::sort(items, items + n, [](const Item &a, const Item &b) { return a.pos < b.pos; });
+    bool storedP = false, storedE = false;
+    for (int t = 0; t < n; ++t) {
+        if (items[t].kind == 1) ST(launch_z(c, sweep, kStZ, zcube));
+        else if (items[t].kind == 2) {
+            ST(launch_p(c, sweep, pops, slots ? slots->Ps : nullptr, slots ? slots->Aps : nullptr, slots ? slots->Bps : nullptr));
+            storedP = true;
+        } else {
+            ST(launch_e(c, sweep, eops, (has3 && !c->Pfixed) ? 1 : 0, slots ? slots->Es : nullptr, slots ? slots->Aes : nullptr,
+                        slots ? slots->Bes : nullptr));
+            storedE = true;
+        }
+    }
+    if (slots) {   // families not touched this sweep (Pfixed, forced orders): plain copies of the state
+        if (!storedP) {
+            if (slots->Ps) CU(cudaMemcpyAsync(slots->Ps, c->P, c->nP * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            if (slots->Aps) CU(cudaMemcpyAsync(slots->Aps, c->Ap, c->nP * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            if (slots->Bps) CU(cudaMemcpyAsync(slots->Bps, c->Bp, c->nP * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (!storedE) {
+            if (slots->Es) CU(cudaMemcpyAsync(slots->Es, c->E, c->nE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            if (slots->Aes) CU(cudaMemcpyAsync(slots->Aes, c->Ae, c->nE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            if (slots->Bes) CU(cudaMemcpyAsync(slots->Bes, c->Be, c->nE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    return SIGNER_OK;
+}
+
+int ensure_rings(signer_chain *c, int eval, int keep_par)
+{
+    const size_t per_sweep = sizeof(double) * (c->nP + c->nE) * (keep_par ? 3 : 2);
+    int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)eval, kRingBytes / per_sweep));
+    if (c->ring_cap >= cap && c->ring_keep >= keep_par) return SIGNER_OK;
+    for (int b = 0; b < 2; ++b) {
+        signer_chain::free_ring(c->ring[b]);
+        Ring &r = c->ring[b];
+        CU(cudaMalloc(&r.Ps, sizeof(double) * c->nP * cap));
+        CU(cudaMalloc(&r.Es, sizeof(double) * c->nE * cap));
+        CU(cudaMalloc(&r.Bps, sizeof(double) * c->nP * cap));
+        CU(cudaMalloc(&r.Bes, sizeof(double) * c->nE * cap));
+        if (keep_par) {
+            CU(cudaMalloc(&r.Aps, sizeof(double) * c->nP * cap));
+            CU(cudaMalloc(&r.Aes, sizeof(double) * c->nE * cap));
+        }
+        CU(cudaEventCreateWithFlags(&r.filled, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r.copied, cudaEventDisableTiming));
+    }
+    c->ring_cap = cap; c->ring_keep = keep_par;
+    return SIGNER_OK;
+}
+
+// copy chunk `chunk` (sweeps r0 .. r0+cnt-1 of the eval phase) from its ring set to the host
+int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signer_outputs *out)
+{
+    Ring &r = c->ring[chunk & 1];
+    CU(cudaStreamWaitEvent(c->copy_stream, r.filled, 0));
+    auto cp = [&](double *dst, const double *src, size_t per) -> int {
+        if (!dst || !src) return SIGNER_OK;
+        CU(cudaMemcpyAsync(dst + per * (size_t)r0, src, sizeof(double) * per * (size_t)cnt, cudaMemcpyDeviceToHost, c->copy_stream));
+        return SIGNER_OK;
+    };
+    ST(cp(out->Ps, r.Ps, c->nP)); ST(cp(out->Es, r.Es, c->nE));
+    ST(cp(out->Bps, r.Bps, c->nP)); ST(cp(out->Bes, r.Bes, c->nE));
+    if (keep_par) { ST(cp(out->Aps, r.Aps, c->nP)); ST(cp(out->Aes, r.Aes, c->nE)); }
+    CU(cudaEventRecord(r.copied, c->copy_stream));
+    return SIGNER_OK;
+}
+
+int fetch_state(signer_chain *c, signer_outputs *out)
+{
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    auto cp = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (!dst) return SIGNER_OK;
+        CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+        return SIGNER_OK;
+    };
+    ST(cp(out->P, c->P, c->nP * 8)); ST(cp(out->Ap, c->Ap, c->nP * 8)); ST(cp(out->Bp, c->Bp, c->nP * 8));
+    ST(cp(out->E, c->E, c->nE * 8)); ST(cp(out->Ae, c->Ae, c->nE * 8)); ST(cp(out->Be, c->Be, c->nE * 8));
+    ST(cp(out->Zin, c->Zin[c->zcur], c->nP * 4)); ST(cp(out->Znj, c->Znj[c->zcur], c->nE * 4));
+    return SIGNER_OK;
+}
+
+int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st, const signer_opts *o, signer_chain **out)
+{
+    if (!st || !o || !out) return fail(SIGNER_ERR_ARG, "null argument");
+    if (o->Zfixed || o->Thetafixed || o->Afixed)
+        return fail(SIGNER_ERR_UNSUPPORTED, "Zfixed/Thetafixed/Afixed=TRUE are not reachable from signeR and not implemented");
+    if (K <= 0 || K > 128) return fail(SIGNER_ERR_ARG, "K must be in 1..128");
+    if ((long long)K * data->J >= (1LL << 31) || (long long)data->I * K >= (1LL << 31)) return fail(SIGNER_ERR_ARG, "K*J and I*K must be below 2^31");
+    if (!st->P || !st->E || !st->Ap || !st->Bp || !st->Ae || !st->Be) return fail(SIGNER_ERR_ARG, "state: P,E,Ap,Bp,Ae,Be must be non-null");
+    CU(cudaSetDevice(data->device));
+    std::unique_ptr<signer_chain> c(new signer_chain());
+    c->data = data; c->device = data->device; c->I = data->I; c->J = data->J; c->Jp = data->Jp; c->K = K;
+    c->nP = (size_t)c->I * K; c->nE = (size_t)K * c->J;
+    c->h = Hyper{o->ap, o->bp, o->ae, o->be, o->lp, o->le, o->var_ap, o->var_ae};
+    c->key = Key{(uint32_t)o->seed, (uint32_t)(o->seed >> 32)};
+    c->sweep0 = o->sweep0; c->Pfixed = o->Pfixed ? 1 : 0;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    auto up = [&](double **dst, const double *src, size_t n) -> int {
+        CU(cudaMalloc(dst, n * sizeof(double)));
+        CU(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        return SIGNER_OK;
+    };
+    ST(up(&c->P, st->P, c->nP)); ST(up(&c->Ap, st->Ap, c->nP)); ST(up(&c->Bp, st->Bp, c->nP));
+    ST(up(&c->E, st->E, c->nE)); ST(up(&c->Ae, st->Ae, c->nE)); ST(up(&c->Be, st->Be, c->nE));
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMalloc(&c->Zin[b], c->nP * sizeof(int)));
+        CU(cudaMalloc(&c->Znj[b], c->nE * sizeof(int)));
+        CU(cudaMemsetAsync(c->Zin[b], 0, c->nP * sizeof(int), c->stream));
+        CU(cudaMemsetAsync(c->Znj[b], 0, c->nE * sizeof(int), c->stream));
+    }
+    c->n_seg = (c->J + kSeg - 1) / kSeg;
+    CU(cudaMalloc(&c->corrE_part, sizeof(double) * (size_t)c->n_seg * c->nP));
+    CU(cudaMalloc(&c->col, sizeof(double) * (size_t)data->n2));
+    CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)data->n2, c->stream));
+    CU(cudaMalloc(&c->tile_counter, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned long long), c->stream));
+    CU(cudaMalloc(&c->stats, 8 * sizeof(double)));
+
+    // launch geometry
+    c->n_rb = (c->I + kZRows - 1) / kZRows;
+    c->n_tiles = c->n_rb * (c->Jp / kZCols);
+    const size_t zsm = z_smem_bytes(K);
+    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+    int occ = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, kZThreads, zsm));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (occ < 1) return fail(SIGNER_ERR_ARG, "z_alloc_fused does not fit on an SM for this K");
+    c->z_grid = std::max(1, std::min(c->n_tiles, occ * sms));
+    const int nkg = (K + 3) / 4;
+    c->kg_per_split = 2;
+    c->ksplit = (nkg + c->kg_per_split - 1) / c->kg_per_split;
+
+    // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device
+    if (st->Z) {
+        double *slab[2] = {nullptr, nullptr};
+        const size_t ns = (size_t)c->I * c->J;
+        CU(cudaMalloc(&slab[0], ns * sizeof(double)));
+        CU(cudaMalloc(&slab[1], ns * sizeof(double)));
+        for (int k = 0; k < K; ++k) {
+            CU(cudaMemcpyAsync(slab[k & 1], st->Z + ns * k, ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            zslab_reduce<<<(c->J + 127) / 128, 128, 0, c->stream>>>(slab[k & 1], c->I, c->J, K, k, c->Zin[0], c->Znj[0]);
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(slab[0])); CU(cudaFree(slab[1]));
+        c->zcur = 0;
+    } else {
+        c->zcur = 0;
+        ST(launch_z(c.get(), c->sweep0, kStZinit, nullptr));
+    }
+    if (!c->Pfixed) {   // W E' of the initial E, in case step 2 comes before step 3
+        Ops none{0, 0u};
+        ST(launch_e(c.get(), c->sweep0, none, 1, nullptr, nullptr, nullptr));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c.release();
+    return SIGNER_OK;
+}
+
+int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *forced, signer_outputs *out)
+{
+    if (burn < 0 || eval < 0) return fail(SIGNER_ERR_ARG, "burn and eval must be non-negative");
+    CU(cudaSetDevice(c->device));
+    keep_par = keep_par ? 1 : 0;
+    if (eval > 0) {
+        ST(ensure_rings(c, eval, keep_par));
+        if (c->ll_cap < eval) {
+            cudaFree(c->ll_ring); c->ll_ring = nullptr; c->ll_cap = 0;
+            CU(cudaMalloc(&c->ll_ring, sizeof(double) * (size_t)eval));
+            c->ll_cap = eval;
+        }
+    }
+    double *zcube = nullptr;
+    if (keep_par && out && out->Zs && eval > 0) {
+        if (!c->Zcube) CU(cudaMalloc(&c->Zcube, sizeof(double) * (size_t)c->I * c->J * c->K));
+        zcube = c->Zcube;
+    }
+    const int total = burn + eval, cap = std::max(1, c->ring_cap);
+    int chunk_r0 = 0;
+    for (int k = 0; k < total; ++k) {
+        const uint32_t sweep = c->sweep0 + (uint32_t)c->sweeps_done;
+        int order[7];
+        if (forced) for (int f = 0; f < 7; ++f) order[f] = forced[(size_t)7 * k + f];
+        else host_perm(((uint64_t)c->key.k1 << 32) | c->key.k0, sweep, order);
+        const bool storing = k >= burn;
+        if (!storing) {
+            ST(enqueue_sweep(c, sweep, order, nullptr, nullptr));
+        } else {
+            const int r = k - burn, chunk = r / cap, slot = r % cap;
+            Ring &rg = c->ring[chunk & 1];
+            if (slot == 0 && chunk >= 2 && out) CU(cudaStreamWaitEvent(c->stream, rg.copied, 0));
+            Slots s;
+            s.Ps = rg.Ps + c->nP * slot; s.Es = rg.Es + c->nE * slot;
+            s.Bps = rg.Bps + c->nP * slot; s.Bes = rg.Bes + c->nE * slot;
+            if (keep_par) { s.Aps = rg.Aps + c->nP * slot; s.Aes = rg.Aes + c->nE * slot; }
+            const bool last = (k == total - 1);
+            // Zs keeps only the latest Z (src/gibbs_2.cpp:323): store the cube in the last sweep only
+            ST(enqueue_sweep(c, sweep, order, &s, last ? zcube : nullptr));
+            ST(launch_loglik(c, c->ll_ring + r));
+            if (slot == cap - 1 || last) {
+                CU(cudaEventRecord(rg.filled, c->stream));
+                if (out) {
+                    if (chunk >= 1) ST(flush_chunk(c, chunk - 1, chunk_r0 - cap, cap, keep_par, out));
+                    if (last) ST(flush_chunk(c, chunk, chunk_r0, slot + 1, keep_par, out));
+                }
+                chunk_r0 += cap;
+            }
+        }
+        c->sweeps_done++;
+    }
+    c->last_eval = eval;
+    if (out && eval > 0) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->copy_stream));
+        if (zcube && out->Zs) {
+            // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined
+            CU(cudaMemcpy(out->Zs, zcube, sizeof(double) * (size_t)c->I * c->J * c->K, cudaMemcpyDeviceToHost));
+        }
+        if (out->loglik || out->bic) {
+            std::vector<double> ll((size_t)eval);
+            CU(cudaMemcpy(ll.data(), c->ll_ring, sizeof(double) * (size_t)eval, cudaMemcpyDeviceToHost));
+            const double pen = (double)c->K * (double)(c->I + c->J) * std::log((double)c->J);   // R/cpp_eBayesNMF.R:186
+            for (int r = 0; r < eval; ++r) {
+                if (out->loglik) out->loglik[r] = ll[r];
+                if (out->bic) out->bic[r] = 2.0 * ll[r] - pen;
+            }
+        }
+    }
+    if (out) ST(fetch_state(c, out));
+    return SIGNER_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *signer_last_error(void) { return g_err.c_str(); }
+int signer_version(void) { return SIGNER_ABI_VERSION; }
+
+int signer_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return -SIGNER_ERR_CUDA; }
+    return n;
+}
+
+int signer_chain_create(const signer_problem *pr, const signer_state *st, const signer_opts *o, signer_chain **chain)
+{
+    g_err.clear();
+    if (!pr || !st || !o || !chain) return fail(SIGNER_ERR_ARG, "null argument");
+    std::shared_ptr<DeviceData> d;
+    ST(upload_data(o->device, pr->I, pr->J, pr->M, pr->W, d));
+    return chain_create(d, pr->K, st, o, chain);
+}
+
+int signer_chain_set_stream(signer_chain *c, void *cuda_stream)
+{
+    if (!c) return fail(SIGNER_ERR_ARG, "null chain");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return SIGNER_OK;
+}
+
+int signer_chain_set_hyper(signer_chain *c, const double h[8])
+{
+    if (!c || !h) return fail(SIGNER_ERR_ARG, "null argument");
+    c->h = Hyper{h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
+    return SIGNER_OK;
+}
+
+int signer_chain_run(signer_chain *c, int32_t burn, int32_t eval, int32_t keep_par, const int32_t *forced, signer_outputs *out)
+{
+    g_err.clear();
+    if (!c) return fail(SIGNER_ERR_ARG, "null chain");
+    return chain_run(c, burn, eval, keep_par, forced, out);
+}
+
+int signer_chain_sync(signer_chain *c)
+{
+    if (!c) return fail(SIGNER_ERR_ARG, "null chain");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    return SIGNER_OK;
+}
+
+int signer_chain_fetch_state(signer_chain *c, signer_outputs *out)
+{
+    if (!c || !out) return fail(SIGNER_ERR_ARG, "null argument");
+    return fetch_state(c, out);
+}
+
+int signer_chain_fetch_stats(signer_chain *c, double stats[8])
+{
+    if (!c || !stats) return fail(SIGNER_ERR_ARG, "null argument");
+    if (c->last_eval <= 0 || c->last_eval > c->ring_cap || !c->ring_keep)
+        return fail(SIGNER_ERR_ARG, "fetch_stats needs a preceding run with keep_par and eval within the device ring");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->stats, 0, 8 * sizeof(double), c->stream));
+    const Ring &r = c->ring[0];
+    const size_t np = c->nP * (size_t)c->last_eval, ne = c->nE * (size_t)c->last_eval;
+    stats_reduce<<<256, 256, 0, c->stream>>>(r.Aps, r.Bps, np, c->stats);
+    stats_reduce<<<1024, 256, 0, c->stream>>>(r.Aes, r.Bes, ne, c->stats + 4);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(stats, c->stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    stats[3] = (double)np; stats[7] = (double)ne;
+    return SIGNER_OK;
+}
+
+int signer_chain_profile(signer_chain *c, int32_t enable, double ms[4], int64_t launches[4])
+{
+    if (!c) return fail(SIGNER_ERR_ARG, "null chain");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k) {
+        double tot = 0;
+        for (auto &pr : c->ev[k]) {
+            float t = 0;
+            cudaEventElapsedTime(&t, pr.first, pr.second);
+            tot += t;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        if (ms) ms[k] = tot;
+        if (launches) launches[k] = (int64_t)c->ev[k].size();
+        c->ev[k].clear();
+    }
+    c->profiling = enable != 0;
+    return SIGNER_OK;
+}
+
+int64_t signer_chain_sweeps(const signer_chain *c) { return c ? c->sweeps_done : -1; }
+
+void signer_chain_destroy(signer_chain *c) { delete c; }
+
+int signer_gibbs_run(const signer_problem *pr, const signer_state *st, const signer_opts *o, signer_outputs *out)
+{
+    g_err.clear();
+    if (!pr || !st || !o || !out) return fail(SIGNER_ERR_ARG, "null argument");
+    signer_chain *c = nullptr;
+    ST(signer_chain_create(pr, st, o, &c));
+    const int rc = chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, out);
+    const std::string keep = g_err;
+    signer_chain_destroy(c);
+    g_err = keep;
+    return rc;
+}
+
+int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W, signer_task *tasks, int32_t n_tasks,
+                       const int32_t *devices, int32_t n_devices)
+{
+    g_err.clear();
+    if (!tasks || n_tasks < 0 || !devices || n_devices <= 0) return fail(SIGNER_ERR_ARG, "bad batch arguments");
+    // longest-first (cost ~ K * sweeps) dealt greedily onto the least-loaded device
+    std::vector<int> idx(n_tasks);
+    for (int t = 0; t < n_tasks; ++t) idx[t] = t;
+    auto cost = [&](int t) { return (double)tasks[t].K * (double)(tasks[t].opts.burn + tasks[t].opts.eval); };
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    std::vector<std::vector<int>> mine(n_devices);
+    std::vector<double> load(n_devices, 0.0);
+    for (int t : idx) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        mine[d].push_back(t); load[d] += cost(t);
+    }
+    std::vector<std::string> errs(n_devices);
+    std::vector<int> rcs(n_devices, SIGNER_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_devices; ++d) {
+        th.emplace_back([&, d]() {
+            if (mine[d].empty()) return;
+            std::shared_ptr<DeviceData> data;
+            int rc = upload_data(devices[d], I, J, M, W, data);
+            if (rc != SIGNER_OK) { rcs[d] = rc; errs[d] = g_err; for (int t : mine[d]) tasks[t].status = rc; return; }
+            for (int t : mine[d]) {
+                signer_task &tk = tasks[t];
+                signer_chain *c = nullptr;
+                rc = chain_create(data, tk.K, &tk.state, &tk.opts, &c);
+                if (rc == SIGNER_OK) {
+                    signer_outputs out{};
+                    out.loglik = tk.loglik; out.bic = tk.bic;
+                    rc = chain_run(c, tk.opts.burn, tk.opts.eval, 0, tk.opts.forced_order, &out);
+                }
+                delete c;
+                tk.status = rc;
+                if (rc != SIGNER_OK && rcs[d] == SIGNER_OK) { rcs[d] = rc; errs[d] = g_err; }
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rcs[d] != SIGNER_OK) return fail(rcs[d], errs[d]);
+    return SIGNER_OK;
+}
+
+// ---- test hooks
+static int test_setup(int device) { CU(cudaSetDevice(device)); return SIGNER_OK; }
+
+int signer_test_math(int32_t fn, const double *x, double *y, int32_t n, int32_t device)
+{
+    g_err.clear();
+    if (!x || !y || n < 0 || fn < 0 || fn > 3) return fail(SIGNER_ERR_ARG, "bad argument");
+    ST(test_setup(device));
+    double *dx = nullptr, *dy = nullptr;
+    CU(cudaMalloc(&dx, sizeof(double) * (size_t)std::max(n, 1))); CU(cudaMalloc(&dy, sizeof(double) * (size_t)std::max(n, 1)));
+    CU(cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    if (n) test_math<<<(n + 127) / 128, 128>>>(fn, dx, dy, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(y, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
+    return SIGNER_OK;
+}
+
+int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, const int32_t *n, const double *p, int32_t *out,
+                         int32_t count, int32_t device)
+{
+    g_err.clear();
+    if (!n || !p || !out || count < 0) return fail(SIGNER_ERR_ARG, "bad argument");
+    ST(test_setup(device));
+    int *dn = nullptr, *dout = nullptr; double *dp = nullptr;
+    const size_t c = (size_t)std::max(count, 1);
+    CU(cudaMalloc(&dn, 4 * c)); CU(cudaMalloc(&dout, 4 * c)); CU(cudaMalloc(&dp, 8 * c));
+    CU(cudaMemcpy(dn, n, 4 * (size_t)count, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dp, p, 8 * (size_t)count, cudaMemcpyHostToDevice));
+    if (count) test_binomial<<<(count + 127) / 128, 128>>>(Key{(uint32_t)seed, (uint32_t)(seed >> 32)}, sweep, stream_id, dn, dp, dout, count);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, 4 * (size_t)count, cudaMemcpyDeviceToHost));
+    cudaFree(dn); cudaFree(dout); cudaFree(dp);
+    return SIGNER_OK;
+}
+
+int signer_test_gamma(uint64_t seed, uint32_t sweep, uint32_t stream_id, const double *shape, const double *rate, double *out,
+                      int32_t count, int32_t device)
+{
+    g_err.clear();
+    if (!shape || !rate || !out || count < 0) return fail(SIGNER_ERR_ARG, "bad argument");
+    ST(test_setup(device));
+    double *ds = nullptr, *dr = nullptr, *dout = nullptr;
+    const size_t c = (size_t)std::max(count, 1);
+    CU(cudaMalloc(&ds, 8 * c)); CU(cudaMalloc(&dr, 8 * c)); CU(cudaMalloc(&dout, 8 * c));
+    CU(cudaMemcpy(ds, shape, 8 * (size_t)count, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dr, rate, 8 * (size_t)count, cudaMemcpyHostToDevice));
+    if (count) test_gamma<<<(count + 127) / 128, 128>>>(Key{(uint32_t)seed, (uint32_t)(seed >> 32)}, sweep, stream_id, ds, dr, dout, count);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, 8 * (size_t)count, cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(dr); cudaFree(dout);
+    return SIGNER_OK;
+}
+
+void signer_test_perm(uint64_t seed, uint32_t sweep, int32_t order[7])
+{
+    int o[7];
+    host_perm(seed, sweep, o);
+    for (int i = 0; i < 7; ++i) order[i] = o[i];
+}
+
+void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    const U4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+} // extern "C"
