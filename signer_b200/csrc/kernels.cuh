@@ -54,10 +54,10 @@ inline size_t z_smem_bytes(int K)
 __global__ void __launch_bounds__(kZThreads) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *P_s = reinterpret_cast<double *>(smem_raw);          // [32][K]
+    int *m_s = reinterpret_cast<int *>(smem_raw);                                   // [32][32], 16-byte aligned for int4
+    double *P_s = reinterpret_cast<double *>(smem_raw + sizeof(int) * kZRows * kZCols);   // [32][K]
     double *E_s = P_s + kZRows * p.K;                            // [K][33]
     int *znj_s = reinterpret_cast<int *>(E_s + p.K * 33);        // [K][128]
-    int *m_s = znj_s + p.K * kZThreads;                          // [32][32]
     __shared__ int tile_sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
