@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs sweeps/s of the B200 sampler on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is ONE full Gibbs sweep (all seven steps of src/gibbs_2.cpp:305-318) of one chain over the
+whole cohort.  Workload (config.workload): BASELINE.json configs[2], the configuration the metric
+is quoted on: synthetic 96 x 10,000 genomes with an opportunity matrix, K = 20, one long chain per
+GPU.  With N > 1 GPUs every rank runs its own independent chain on the same cohort shape (the
+path shards by chains/candidates, no data-path collective): weak scaling.
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  value            burn-in sweeps/s, chain resident in HBM, CUDA events on the launching stream
+  eval_value       evaluation sweeps/s (samples into the device ring + log-likelihood every sweep)
+  e2e              sweeps/s through the reference-shaped call GibbsSamplerCpp(...) with HOST arrays:
+                   M, W, the I x J x K cube Z and the state go in, the sample cubes come back
+                   (burn = eval = K/2, keep_par = FALSE: the reference's model-selection call,
+                   R/signeR.R:164-168), host<->device copies inside the timed region
+  roofline         dominant kernel z_alloc_fused: algorithmic bytes per launch / mean launch time
+  cpu_baseline     the CPU oracle (oracle/, a port: the reference cannot be built here) on this box
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gibbs_sweeps_per_s"
+UNIT = "sweeps/s"
+WORKLOADS = {
+    "cfg3_96x10000_K20": dict(K=20, desc="synthetic 96x10000 genomes (pan-TCGA scale) with opportunity matrix, K=20, single long chain"),
+    "cfg2_96x560": dict(K=10, desc="synthetic 96x560 genomes (ICGC-breast scale), K=10"),
+    "cfg5_96x100000": dict(K=40, desc="synthetic 96x100000 genomes, K=40"),
+    "cfg4_1536x20000_K30": dict(K=30, desc="synthetic 1536x20000, K=30"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_sweep_rate(M, W, K, seconds_target, seed=1):
+    """Time the CPU oracle on a bounded sample: full sweeps over the first Js genomes (cost is linear
+    in genomes), scaled back to the full cohort.  Returns (full-cohort sweeps/s, description)."""
+    from oracle import oracle as O
+    from signer_b200 import synth
+    I, J = M.shape
+    Js = min(J, 200)
+    st = synth.init_state(I, Js, K, seed=seed)
+    t0 = time.perf_counter()
+    O.gibbs_run(M[:, :Js], W[:, :Js], None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=1, eval=0,
+                seed=seed, want_Z=False)
+    per_col = (time.perf_counter() - t0) / 2.0 / Js          # init allocation + 1 sweep
+    # choose sample: nsw sweeps over Js columns ~ seconds_target
+    nsw = 4
+    Js = int(max(32, min(J, seconds_target / (nsw + 1) / per_col)))
+    st = synth.init_state(I, Js, K, seed=seed)
+    Msub, Wsub = np.asfortranarray(M[:, :Js]), np.asfortranarray(W[:, :Js])
+    t0 = time.perf_counter()
+    O.gibbs_run(Msub, Wsub, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=0, eval=0, seed=seed, want_Z=False)
+    t_init = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.gibbs_run(Msub, Wsub, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=nsw, eval=0, seed=seed, want_Z=False)
+    t_run = time.perf_counter() - t0 - t_init
+    per_sweep_full = t_run / nsw * (J / Js)
+    return 1.0 / per_sweep_full, "%d burn-in sweeps of the oracle over the first %d of %d genomes, scaled by %d/%d" % (nsw, Js, J, J, Js)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on this box's host cores.
+    The reference itself needs R + Rcpp + RcppArmadillo (absent), so this times oracle/_ref when the
+    reference sources could be compiled against the stand-in headers, else the oracle port.  One
+    chain = one thread (the reference's native code is single-threaded, R/Optimal_sigs.R:3-8 only
+    parallelises over candidates)."""
+    if rank != 0:
+        return
+    from signer_b200 import synth
+    M, W, _, _ = synth.named(args.workload)
+    K = WORKLOADS[args.workload]["K"]
+    I, J = M.shape
+    from oracle import oracle as O
+    kind = "port"
+    runner = O.gibbs_run
+    try:
+        from oracle import ref_runner
+        if ref_runner.available():
+            runner = ref_runner.gibbs_run
+            kind = "reference"
+    except Exception:
+        pass
+    # size the per-step sample so warmup+steps finish in about two minutes
+    Js0 = min(J, 128)
+    st = synth.init_state(I, Js0, K, seed=3)
+    t0 = time.perf_counter()
+    runner(np.asfortranarray(M[:, :Js0]), np.asfortranarray(W[:, :Js0]), None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"],
+           burn=2, eval=0, seed=3, want_Z=False)
+    per_col_sweep = (time.perf_counter() - t0) / 3.0 / Js0
+    budget = 120.0
+    Js = int(max(16, min(J, budget / max(1, args.steps + args.warmup) / per_col_sweep)))
+    st = synth.init_state(I, Js, K, seed=3)
+    Msub, Wsub = np.asfortranarray(M[:, :Js]), np.asfortranarray(W[:, :Js])
+    t0 = time.perf_counter()
+    runner(Msub, Wsub, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=args.warmup, eval=0, seed=3, want_Z=False)
+    t_warm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    runner(Msub, Wsub, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=args.warmup + args.steps, eval=0, seed=3, want_Z=False)
+    t_all = time.perf_counter() - t0
+    dt = max(t_all - t_warm, 1e-9)
+    ms_step_sample = dt / args.steps * 1e3
+    value = args.steps / dt * (Js / J)
+    sample = ("each step = one Gibbs sweep over the first %d of %d genomes (cost linear in genomes); "
+              "value scaled by %d/%d to the full cohort" % (Js, J, Js, J))
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step_sample * (J / Js), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=args.workload, description=WORKLOADS[args.workload]["desc"], I=I, J=J, K=K),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind=kind, sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3_96x10000_K20", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import signer_b200 as sg
+    from signer_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist_on:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = WORKLOADS[args.workload]
+    K = wl["K"]
+    M, W, _, _ = synth.named(args.workload)
+    I, J = M.shape
+    st = synth.init_state(I, J, K, seed=1000 * K + rank)
+    hyper = synth.hyper_tuple()
+    chain = sg.Chain(M, W, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], hyper, seed=1000 * K + rank, device=local)
+    stream = torch.cuda.current_stream()
+    chain.set_stream(stream.cuda_stream)
+
+    # ---------------- value: burn-in sweeps, device resident
+    chain.run(burn=args.warmup, fetch=False)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = chain.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    chain.run(burn=args.steps, fetch=False)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = chain.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---------------- evaluation sweeps (samples + log-likelihood kept on the device)
+    n_eval = min(args.steps, 500)
+    chain.run(eval=8, fetch=False)
+    barrier()
+    e0.record(stream)
+    chain.run(eval=n_eval, keep_par=False, fetch=False)
+    e1.record(stream)
+    barrier()
+    ms_eval = max_over_ranks(e0.elapsed_time(e1))
+    eval_value = world * n_eval / (ms_eval * 1e-3)
+
+    # ---------------- per-kernel times: second pass of burn-in sweeps with events around every launch
+    n_prof = min(args.steps, 500)
+    chain.profile(True)
+    chain.run(burn=n_prof, fetch=False)
+    prof = chain.profile(False)
+    kz = prof["z_alloc_fused"]
+    z_ms = kz["ms"] / max(1, kz["launches"])
+    tot_prof_ms = sum(v["ms"] for v in prof.values())
+    z_bytes = 4.0 * I * J + 12.0 * K * (I + J)                  # M int32 in; P,E in; Zin,Znj out
+    peak, peak_src = peaks()
+    achieved = z_bytes / (z_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "z_alloc_fused_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = dict(bound="hbm", kernel="z_alloc_fused", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=z_bytes, ms_per_launch=z_ms,
+                    share_of_sweep=kz["ms"] / tot_prof_ms if tot_prof_ms else None,
+                    timing="second pass of %d burn-in sweeps with CUDA events around every launch" % n_prof,
+                    note="issue/RNG-bound, working set L2-resident (SURVEY.md 8d): HBM fraction reported as defined; "
+                         "see draws_per_s for the rate that binds")
+    b_sweep = 20.0 * I * J + 104.0 * K * (I + J)
+    per_rank_sps = args.steps / (ms * 1e-3)
+    kernels_ms = {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in prof.items()}
+    chain.set_stream(None)
+
+    # ---------------- e2e: the reference-shaped stateless call with host arrays
+    e2e = None
+    if not args.no_e2e:
+        zrun = sg.GibbsSamplerCpp(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *hyper, 0, 1,
+                                  False, False, False, False, True, seed=5, device=local)
+        Z0 = np.asfortranarray(zrun[0][:, :, :, 0])
+        del zrun
+        nb = max(1, args.steps // 2)
+        ne = max(1, args.steps - nb)
+        sg.GibbsSamplerCpp(M, W, Z0, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *hyper, 3, 3,
+                           False, False, False, False, False, seed=6, device=local)      # warm-up of the call path
+        barrier()
+        t0 = time.perf_counter()
+        res = sg.GibbsSamplerCpp(M, W, Z0, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *hyper, nb, ne,
+                                 False, False, False, False, False, seed=7, device=local)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        h2d = 8.0 * (2 * I * J + I * J * K + 3 * (I * K + K * J)) + 4.0 * I * J * 0
+        d2h = 8.0 * ne * 2 * (I * K + K * J) + 16.0 * ne + 8.0 * 3 * (I * K + K * J) + 4.0 * (I * K + K * J)
+        e2e = dict(value=world * (nb + ne) / dt, unit=UNIT, h2d_bytes_per_step=h2d / (nb + ne), d2h_bytes_per_step=d2h / (nb + ne),
+                   call="GibbsSamplerCpp(M,W,Z,P,E,Ap,Bp,Ae,Be,...,burn=%d,eval=%d,keep_par=FALSE) with host arrays; "
+                        "pageable host memory as R hands it over" % (nb, ne), seconds=dt,
+                   median_bic=float(np.median(res.bic)))
+        del res
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sample = cpu_sweep_rate(M, W, K, seconds_target=15.0)
+        cpu = dict(value=v, unit=UNIT, cores=1, kind="port", sample=sample)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic",
+                    config=dict(workload=args.workload, description=wl["desc"], I=I, J=J, K=K, chains_per_gpu=1,
+                                l2="working set (M int32 + W f64 = 11.5 MB, state 5 MB) is L2-resident by design: a chain "
+                                   "iterates over the same cohort every sweep, so no L2 flush between steps"),
+                    clocks=clk, e2e=e2e, gpu_launches=int(launches) * world,
+                    eval_value=eval_value, eval_ms_per_step=ms_eval / n_eval,
+                    roofline=roofline,
+                    roofline_sweep=dict(algorithmic_bytes_per_sweep=b_sweep, achieved=b_sweep * per_rank_sps / 1e9, peak=peak,
+                                        unit="GB/s", frac=b_sweep * per_rank_sps / 1e9 / peak),
+                    kernel_ms=kernels_ms,
+                    draws_per_s=dict(binomial_upper_bound=per_rank_sps * I * J * (K - 1), gamma=per_rank_sps * 3 * K * (I + J)),
+                    cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    chain.close()
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

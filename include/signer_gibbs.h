@@ -117,6 +117,8 @@ int signer_chain_fetch_stats(signer_chain *chain, double stats[8]);
 int signer_chain_profile(signer_chain *chain, int32_t enable, double ms[4], int64_t launches[4]);
 /* Number of sweeps run so far (next Philox sweep index = sweep0 + this). */
 int64_t signer_chain_sweeps(const signer_chain *chain);
+/* Number of kernels this chain has launched so far (memsets and copies not counted). */
+int64_t signer_chain_launches(const signer_chain *chain);
 void signer_chain_destroy(signer_chain *chain);
 
 /* Candidates x chains over several GPUs of one box (replaces the multisession futures of

@@ -126,6 +126,7 @@ struct signer_chain {
     Key key{};
     uint32_t sweep0 = 0;
     int64_t sweeps_done = 0;
+    int64_t launches = 0;
     int Pfixed = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     Ring ring[2];
@@ -208,6 +209,7 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     }
     CU(cudaGetLastError());
     c->z_launches++;
+    c->launches++;
     c->zcur = tgt;
     return SIGNER_OK;
 }
@@ -223,6 +225,7 @@ int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double
         ProfScope ps(c, 1);
         p_family<<<(p.IK + 127) / 128, 128, 0, c->stream>>>(p);
     }
+    c->launches++;
     CU(cudaGetLastError());
     return SIGNER_OK;
 }
@@ -240,6 +243,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
         ProfScope ps(c, 2);
         e_family<<<dim3(c->n_seg, c->ksplit), kEThreads, e_smem_bytes(c->kg_per_split), c->stream>>>(p);
     }
+    c->launches++;
     CU(cudaGetLastError());
     return SIGNER_OK;
 }
@@ -254,6 +258,7 @@ int launch_loglik(signer_chain *c, double *out)
         loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
         tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out);
     }
+    c->launches += 2;
     CU(cudaGetLastError());
     return SIGNER_OK;
 }
@@ -622,6 +627,7 @@ int signer_chain_profile(signer_chain *c, int32_t enable, double ms[4], int64_t 
 }
 
 int64_t signer_chain_sweeps(const signer_chain *c) { return c ? c->sweeps_done : -1; }
+int64_t signer_chain_launches(const signer_chain *c) { return c ? c->launches : -1; }
 
 void signer_chain_destroy(signer_chain *c) { delete c; }
 

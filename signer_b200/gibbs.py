@@ -214,6 +214,10 @@ class Chain:
     def sweeps(self):
         return int(_lib.lib().signer_chain_sweeps(self._h))
 
+    @property
+    def launches(self):
+        return int(_lib.lib().signer_chain_launches(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().signer_chain_destroy(self._h)
