@@ -212,6 +212,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
+        torch.cuda.synchronize()
         if dist_on:
             dist.barrier()
         torch.cuda.synchronize()
@@ -230,7 +231,9 @@ def main():
     st = synth.init_state(I, J, K, seed=1000 * K + rank)
     hyper = synth.hyper_tuple()
     chain = sg.Chain(M, W, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], hyper, seed=1000 * K + rank, device=local)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the chain launches on it, torch events time it
+    stream = torch.cuda.Stream(device=local)
+    assert stream.cuda_stream != 0
     chain.set_stream(stream.cuda_stream)
 
     # ---------------- value: burn-in sweeps, device resident

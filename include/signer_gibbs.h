@@ -95,7 +95,8 @@ typedef struct signer_chain signer_chain;
 int signer_chain_create(const signer_problem *problem, const signer_state *state,
                         const signer_opts *opts, signer_chain **chain);
 /* Launch on an existing CUDA stream (a cudaStream_t) instead of the chain's own; pass NULL to
- * restore.  Lets a host framework time the chain with its own events. */
+ * restore (so the legacy default stream, whose handle is NULL, cannot be selected).  Lets a host
+ * framework time the chain with its own events. */
 int signer_chain_set_stream(signer_chain *chain, void *cuda_stream);
 /* Update the hyper-hyperparameters between EM iterations (ap,bp,ae,be,lp,le,var_ap,var_ae). */
 int signer_chain_set_hyper(signer_chain *chain, const double hyper[8]);
@@ -141,8 +142,8 @@ int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W,
  * tests can compare them bit for bit with the oracle.  n values each; fn: 0 log, 1 exp, 2 lgamma,
  * 3 ppnd16. */
 int signer_test_math(int32_t fn, const double *x, double *y, int32_t n, int32_t device);
-/* binomial(n[i], p[i]) drawn from stream (seed, sweep, stream_id, element=i) */
-int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, const int32_t *n,
+/* binomial(n[i], p[i]) drawn as conditional binomial number `kstep` of stream (seed, sweep, stream_id, element=i) */
+int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, int32_t kstep, const int32_t *n,
                          const double *p, int32_t *out, int32_t count, int32_t device);
 /* gamma(shape[i], rate[i]) drawn from stream (seed, sweep, stream_id, element=i) */
 int signer_test_gamma(uint64_t seed, uint32_t sweep, uint32_t stream_id, const double *shape,

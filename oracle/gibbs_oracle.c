@@ -33,11 +33,15 @@
  *   stream ids: 0 permutation, 1..7 Gibbs steps, 8 initial Z
  *   element: step 1/8: i + I*j ; P family (2,4,6): i + I*k ; E family (3,5,7): k + K*j
  *   u53(w0,w1) = (2*((w0>>6)<<26 | (w1>>6)) + 1) * 2^-53       in (0,1)
- *   step 1 consumes uniforms sequentially from blocks 0,1,2,... (two per block)
+ *   step 1, cells with count n <= 16: direct method, n categorical draws; draw t uses half (t&1) of
+ *                block (t>>1): x = u*S, class = first k < K-1 with x < c_k, c_k = c_{k-1} + P[i,k]*E[k,j],
+ *                else the last class.  Larger cells: sequential conditional binomials (rmultinom):
+ *   step 1, conditional binomial of class k: the inversion uniform is half (k&1) of block (k>>1);
+ *                BTRS attempt t of class k reads block 0x1000 + (k<<8) + t (U from the first half, V second)
  *   gamma draws: Marsaglia-Tsang attempt t uses block t: x = ppnd16(u(w0,w1)), accept test u(w2,w3);
  *                block 0xFFFFFFFF gives (boost uniform for shape<1, MH acceptance uniform)
- *   binomial(n,pp): p=min(pp,1-pp); n*p<10 -> inversion from q^n (binary powering);
- *                   else Hormann BTRS; flip back if pp>0.5
+ *   binomial(n,pp): p=min(pp,1-pp); n*p<10 -> inversion from q^n (binary powering), recurrence
+ *                   r <- (r * (s*(n-x+1))) * (1/x); else Hormann BTRS; flip back if pp>0.5
  *   fp reductions: PE = fma chain over k; corrP = fma chain over i; corrE = 128-column segment
  *                  fma chains, segments added in ascending order (per shard, shards ascending);
  *                  loglik = per-column sums in 32-row chunks (chunks added in order), then a
@@ -53,6 +57,8 @@
 #define BINV_MAX 10.0
 #define TINY 1e-160
 #define AUX_BLOCK 0xFFFFFFFFu
+#define BTRS_BLOCK0 0x1000u
+#define NDIRECT 16
 
 enum { ST_PERM = 0, ST_Z = 1, ST_P = 2, ST_E = 3, ST_BP = 4, ST_BE = 5, ST_AP = 6, ST_AE = 7, ST_ZINIT = 8 };
 
@@ -85,15 +91,12 @@ double oracle_u53(uint32_t w0, uint32_t w1)
 typedef struct {
     uint32_t key[2];
     uint32_t elem, stream, sweep;
-    uint32_t block;      /* next block to generate */
-    int have;            /* spare uniform available */
-    double spare;
 } ustream;
 
 static void us_init(ustream *s, uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem)
 {
     s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
-    s->elem = elem; s->stream = stream; s->sweep = sweep; s->block = 0; s->have = 0; s->spare = 0;
+    s->elem = elem; s->stream = stream; s->sweep = sweep;
 }
 
 static void us_block(const ustream *s, uint32_t block, double *u0, double *u1)
@@ -102,15 +105,6 @@ static void us_block(const ustream *s, uint32_t block, double *u0, double *u1)
     oracle_philox(ctr, s->key, w);
     *u0 = oracle_u53(w[0], w[1]);
     *u1 = oracle_u53(w[2], w[3]);
-}
-
-static double us_next(ustream *s)
-{
-    if (s->have) { s->have = 0; return s->spare; }
-    double a, b;
-    us_block(s, s->block++, &a, &b);
-    s->spare = b; s->have = 1;
-    return a;
 }
 
 /* ------------------------------------------------------------------ deterministic math */
@@ -260,7 +254,7 @@ static double btrs_fc(double k)
 /* Binomial(n, pp), n >= 1, 0 < pp < 1.  Small n*p: sequential-search inversion ("BINV",
  * Kachitvichyanukul & Schmeiser 1988) started from q^n.  Otherwise: Hormann's BTRS
  * ("The generation of binomial random variates", J. Stat. Comput. Simul. 46, 1993). */
-static int binomial_draw(ustream *s, int n, double pp)
+static int binomial_draw(const ustream *s, int kstep, int n, double pp)
 {
     int flip = pp > 0.5;
     double p = flip ? 1.0 - pp : pp;
@@ -276,13 +270,18 @@ static int binomial_draw(ustream *s, int n, double pp)
             if (!e) break;
             b = b * b;
         }
-        double sr = p / q;
-        double u = us_next(s);
+        double u0, u1;
+        us_block(s, (uint32_t)kstep >> 1, &u0, &u1);
+        double u = (kstep & 1) ? u1 : u0;
         x = 0;
-        while (u >= r && x < n) {
-            u = u - r;
-            x += 1;
-            r = (r * (sr * (double)(n - x + 1))) / (double)x;
+        if (u >= r) {
+            double sr = p / q;
+            double xd = 0.0;
+            while (u >= r && x < n) {
+                u = u - r;
+                x += 1; xd += 1.0;
+                r = (r * (sr * (nd - xd + 1.0))) * (1.0 / xd);
+            }
         }
     } else {
         double spq = sqrt(nd * p * q);
@@ -293,11 +292,14 @@ static int binomial_draw(ustream *s, int n, double pp)
         double alpha = (2.83 + 5.1 / b) * spq;
         double r = p / q;
         double m = floor((nd + 1.0) * p);
-        for (;;) {
-            double U = us_next(s) - 0.5;
-            double V = us_next(s);
+        double kd = 0.0;
+        x = -1;
+        for (uint32_t t = 0; t < 256; t++) {
+            double U, V;
+            us_block(s, BTRS_BLOCK0 + ((uint32_t)kstep << 8) + t, &U, &V);
+            U = U - 0.5;
             double us = 0.5 - fabs(U);
-            double kd = floor((2.0 * a / us + b) * U + c);
+            kd = floor((2.0 * a / us + b) * U + c);
             if (us >= 0.07 && V <= vr) { x = (int)kd; break; }
             if (kd < 0.0 || kd > nd) continue;
             double lv = oracle_log(V * alpha / (a / (us * us) + b));
@@ -307,14 +309,15 @@ static int binomial_draw(ustream *s, int n, double pp)
                       + btrs_fc(m) + btrs_fc(nd - m) - btrs_fc(kd) - btrs_fc(nd - kd);
             if (lv <= ub) { x = (int)kd; break; }
         }
+        if (x < 0) x = (kd < 0.0) ? 0 : (kd > nd) ? n : (int)kd;     /* 256 rejections: never in practice */
     }
     return flip ? n - x : x;
 }
 
-int oracle_binomial(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem, int n, double pp)
+int oracle_binomial(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem, int kstep, int n, double pp)
 {
     ustream s; us_init(&s, seed, sweep, stream, elem);
-    return binomial_draw(&s, n, pp);
+    return binomial_draw(&s, kstep, n, pp);
 }
 
 /* Gamma(shape, rate) with the clamps of one_gamma_dist (src/gibbs_2.cpp:39-43);
@@ -384,9 +387,10 @@ typedef struct {
 
 #define ZIDX(c, s, g, m) ((size_t)(s) + (size_t)(c)->I * ((size_t)(g) + (size_t)(c)->J * (size_t)(m)))
 
-/* One cell of step 1: Z[s,g,.] ~ Multinomial(trunc(M[s,g]), P[s,.] o E[.,g] / sum), drawn as R's
- * rmultinom does (sequential conditional binomials in k order; zero-probability skip; pp<1 test;
- * early exit at n<=0; remainder to the last class).  z has stride zs.  src/gibbs_2.cpp:94-101. */
+/* One cell of step 1: Z[s,g,.] ~ Multinomial(trunc(M[s,g]), P[s,.] o E[.,g] / sum).  Counts above
+ * NDIRECT are drawn as R's rmultinom does (sequential conditional binomials in k order;
+ * zero-probability skip; pp<1 test; early exit at n<=0; remainder to the last class); smaller
+ * counts by n categorical draws (same distribution, cost O(n log K) instead of O(K)).  z has stride zs.  src/gibbs_2.cpp:94-101. */
 static void multinomial_cell(uint64_t seed, uint32_t sweep, uint32_t stream, int I, int K,
                              int s, int g, double Mval, const double *P, const double *E,
                              double *z, size_t zs)
@@ -401,12 +405,29 @@ static void multinomial_cell(uint64_t seed, uint32_t sweep, uint32_t stream, int
         return;
     }
     ustream us; us_init(&us, seed, sweep, stream, (uint32_t)(s + I * g));
+    if (n <= NDIRECT) {
+        /* per-count algorithm switch: small counts use the direct method -- n categorical draws,
+         * draw t from half (t&1) of block (t>>1): class = first k with u*S < cumulative sum */
+        for (int t = 0; t < n; t++) {
+            double u0, u1;
+            us_block(&us, (uint32_t)t >> 1, &u0, &u1);
+            double x = ((t & 1) ? u1 : u0) * S;
+            double c = 0.0;
+            int cls = K - 1;
+            for (int m = 0; m < K - 1; m++) {
+                c = c + P[s + (size_t)I * m] * E[m + (size_t)K * g];
+                if (x < c) { cls = m; break; }
+            }
+            z[cls * zs] += 1.0;
+        }
+        return;
+    }
     double rem = S;
     for (int m = 0; m < K - 1; m++) {
         double prob = P[s + (size_t)I * m] * E[m + (size_t)K * g];
         if (prob != 0.0) {
             double pp = prob / rem;
-            int zz = (pp > 0.0 && pp < 1.0) ? binomial_draw(&us, n, pp) : n;
+            int zz = (pp > 0.0 && pp < 1.0) ? binomial_draw(&us, m, n, pp) : n;
             z[m * zs] = (double)zz;
             n -= zz;
         }

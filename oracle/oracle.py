@@ -40,7 +40,7 @@ def lib():
         L.oracle_u53.restype = d
         L.oracle_u53.argtypes = [u32, u32]
         L.oracle_binomial.restype = i32
-        L.oracle_binomial.argtypes = [u64, u32, u32, u32, i32, d]
+        L.oracle_binomial.argtypes = [u64, u32, u32, u32, i32, i32, d]
         L.oracle_gamma.restype = d
         L.oracle_gamma.argtypes = [u64, u32, u32, u32, d, d]
         L.oracle_perm.restype = None

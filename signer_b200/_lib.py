@@ -102,7 +102,7 @@ def lib():
     L.signer_test_math.restype = C.c_int
     L.signer_test_math.argtypes = [C.c_int32, dp, dp, C.c_int32, C.c_int32]
     L.signer_test_binomial.restype = C.c_int
-    L.signer_test_binomial.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, ip, dp, ip, C.c_int32, C.c_int32]
+    L.signer_test_binomial.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, ip, dp, ip, C.c_int32, C.c_int32]
     L.signer_test_gamma.restype = C.c_int
     L.signer_test_gamma.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, dp, dp, dp, C.c_int32, C.c_int32]
     L.signer_test_perm.restype = None

@@ -1,4 +1,4 @@
-// draws.cuh -- device primitives of the draw specification v1.
+// draws.cuh -- device primitives of the draw specification v2.
 //
 // Everything here is built from IEEE-754 correctly rounded fp64 operations (+ - * / sqrt fma) in
 // a fixed order, plus integer arithmetic, so that results are bit-identical to any other
@@ -20,6 +20,7 @@ namespace sg {
 constexpr double kTiny = 1e-160;              // pow(10,-160) clamps, src/gibbs_2.cpp:40-41,150,166,182,223
 constexpr double kBinvMax = 10.0;             // n*p below this: inversion; otherwise BTRS
 constexpr uint32_t kAuxBlock = 0xFFFFFFFFu;   // block holding (boost uniform, MH uniform)
+constexpr uint32_t kBtrsBlock0 = 0x1000u;     // first BTRS block of a step-1 stream
 constexpr int kSeg = 128;                     // columns per corrE segment
 
 enum Stream : uint32_t { kStPerm = 0, kStZ = 1, kStP = 2, kStE = 3, kStBp = 4, kStBe = 5, kStAp = 6, kStAe = 7, kStZinit = 8 };
@@ -56,29 +57,18 @@ SG_D double u53(uint32_t w0, uint32_t w1)
 
 struct Key { uint32_t k0, k1; };
 
-// A stream is addressed by (key, sweep, stream id, element); blocks are numbered from 0.
+// A stream is addressed by (key, sweep, stream id, element); its blocks are addressed directly.
 struct UStream {
     uint32_t k0, k1, elem, stream, sweep;
-    uint32_t block;
-    bool have;
-    double spare;
     SG_D void init(Key k, uint32_t sw, uint32_t st, uint32_t e)
     {
-        k0 = k.k0; k1 = k.k1; elem = e; stream = st; sweep = sw; block = 0; have = false; spare = 0.0;
+        k0 = k.k0; k1 = k.k1; elem = e; stream = st; sweep = sw;
     }
     SG_D void pair(uint32_t b, double &u0, double &u1) const
     {
         const U4 w = philox4x32_10(b, elem, stream, sweep, k0, k1);
         u0 = u53(w.x, w.y);
         u1 = u53(w.z, w.w);
-    }
-    SG_D double next()
-    {
-        if (have) { have = false; return spare; }
-        double a, b;
-        pair(block++, a, b);
-        spare = b; have = true;
-        return a;
     }
 };
 
@@ -220,14 +210,27 @@ SG_D double btrs_fc(double k)
     return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / sq) / sq) / kp1;
 }
 
-// Binomial(n, pp) for n >= 1, 0 < pp < 1.
-SG_D int binomial_draw(UStream &s, int n, double pp)
+// 1/x for x = 1..255 (entry 0 unused): the inversion recurrence multiplies by the correctly
+// rounded reciprocal instead of dividing.
+struct RcpTab {
+    double v[256];
+    constexpr RcpTab() : v{} { for (int i = 1; i < 256; ++i) v[i] = 1.0 / (double)i; }
+};
+__device__ const RcpTab g_rcp_tab = RcpTab();
+
+SG_D double rcp_int(int x, double xd) { return x < 256 ? __ldg(&g_rcp_tab.v[x]) : 1.0 / xd; }
+
+// Binomial(n, pp) for n >= 1, 0 < pp < 1, conditional binomial number `kstep` of its cell.
+// u_binv: the inversion uniform = half (kstep&1) of block (kstep>>1) of the cell's stream (the
+// caller generates it, warp-converged, once per two steps).  BTRS attempt t reads block
+// kBtrsBlock0 + (kstep<<8) + t of the same stream.
+SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double pp)
 {
     const bool flip = pp > 0.5;
     const double p = flip ? 1.0 - pp : pp;
     const double q = 1.0 - p;
     const double nd = (double)n;
-    int x;
+    int x = 0;
     if (nd * p < kBinvMax) {
         // inversion by sequential search from P(X=0) = q^n (binary powering)
         double r = 1.0, b = q;
@@ -238,14 +241,15 @@ SG_D int binomial_draw(UStream &s, int n, double pp)
             if (!e) break;
             b = b * b;
         }
-        const double sr = p / q;
-        double u = s.next();
-        double xd = 0.0;
-        x = 0;
-        while (u >= r && x < n) {
-            u = u - r;
-            x += 1; xd += 1.0;
-            r = (r * (sr * (nd - xd + 1.0))) / xd;
+        double u = u_binv;
+        if (u >= r) {
+            const double sr = p / q;
+            double xd = 0.0;
+            while (u >= r && x < n) {
+                u = u - r;
+                x += 1; xd += 1.0;
+                r = (r * (sr * (nd - xd + 1.0))) * rcp_int(x, xd);
+            }
         }
     } else {
         // Hormann's BTRS: transformed rejection with squeeze
@@ -257,11 +261,14 @@ SG_D int binomial_draw(UStream &s, int n, double pp)
         const double alpha = (2.83 + 5.1 / b) * spq;
         const double r = p / q;
         const double m = floor((nd + 1.0) * p);
-        for (;;) {
-            const double U = s.next() - 0.5;
-            const double V = s.next();
+        double kd = 0.0;
+        x = -1;
+        for (uint32_t t = 0; t < 256; ++t) {
+            double U, V;
+            s.pair(kBtrsBlock0 + ((uint32_t)kstep << 8) + t, U, V);
+            U = U - 0.5;
             const double us = 0.5 - fabs(U);
-            const double kd = floor((2.0 * a / us + b) * U + c);
+            kd = floor((2.0 * a / us + b) * U + c);
             if (us >= 0.07 && V <= vr) { x = (int)kd; break; }
             if (kd < 0.0 || kd > nd) continue;
             const double lv = det_log(V * alpha / (a / (us * us) + b));
@@ -271,6 +278,7 @@ SG_D int binomial_draw(UStream &s, int n, double pp)
                             + btrs_fc(m) + btrs_fc(nd - m) - btrs_fc(kd) - btrs_fc(nd - kd);
             if (lv <= ub) { x = (int)kd; break; }
         }
+        if (x < 0) x = (kd < 0.0) ? 0 : (kd > nd) ? n : (int)kd;
     }
     return flip ? n - x : x;
 }

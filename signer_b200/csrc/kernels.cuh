@@ -21,9 +21,6 @@
 namespace sg {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kZRows = 32;        // rows per z_alloc tile (4 warps x 8 rows)
-constexpr int kZCols = 32;        // columns per z_alloc tile (one per lane)
-constexpr int kZThreads = 128;
 constexpr int kEThreads = 256;    // e_family: 128 columns x 2 k-group lanes
 constexpr int kLLChunk = 32;      // rows per log-likelihood chunk
 
@@ -31,118 +28,186 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 
 // ------------------------------------------------------------------------------------------------
 // K1  z_alloc_fused : replaces gibbs_step1 (src/gibbs_2.cpp:85-103) + cube_sum_j/_i (:9-28)
+//
+// One thread per (context, genome) cell; a warp owns a unit of 32 genomes x 4 context rows and
+// works alone (private shared memory, no block barrier; units are claimed heaviest-first from a
+// global counter).  Per row the 32 lanes draw their cells' allocations with the per-count switch
+// of the draw specification:
+//   n <= 16 : direct method -- n categorical draws by binary search in the lane's cumulative
+//             P[i,.] o E[.,j]; the Philox block of draws (t, t+1) is generated warp-converged;
+//   n  > 16 : R's rmultinom structure -- the K classes in lockstep, one conditional binomial each.
+// The class counts are reduced on the spot: over the 32 genomes with one REDUX (-> Zin, one
+// integer atomic per row/class/warp) and per lane over the unit's rows (-> Znj, shared memory,
+// one atomic per class/genome/unit).  Z itself is never written (except, on request, the final
+// sweep's cube for the reference's `Zs`).
+//
+// Genomes are visited in a kernel-private order, sorted by mutation burden (col_id maps a
+// position to the original genome): neighbouring lanes then hold similar counts, so they take the
+// same sampler branch with similar trip counts.  Random streams, Znj and the cube are addressed
+// by the ORIGINAL genome index, so the order cannot change any result.
 // ------------------------------------------------------------------------------------------------
+constexpr int kZUnitRows = 4;     // context rows per unit
+constexpr int kZWarps = 2;        // independent warps per block
+constexpr int kNDirect = 16;      // largest count drawn by the direct method
+
 struct ZParams {
     int I, J, Jp, K;
-    const int *M;               // [I][Jp]
+    const int *M;               // [I][Jp], columns in burden order
+    const int *col_id;          // [Jp] original genome of each position, -1 for padding
     const double *P, *E;
     int *Zin, *Znj;             // accumulated with integer atomics; zeroed by the previous launch
     int *Zin_next, *Znj_next;   // the other half of the ping-pong, zeroed by this launch
     double *Zcube;              // optional I x J x K (pre-zeroed) for the last Z (src/gibbs_2.cpp:323)
-    unsigned long long *tile_counter;
-    unsigned long long tile_base;
-    int n_rb, n_tiles;
+    unsigned long long *unit_counter;
+    unsigned long long unit_base;
+    int n_rc, n_units;          // row chunks per column tile, units in total
+    int warp_smem;              // bytes of shared memory per warp
     Key key;
     uint32_t sweep, stream;
 };
 
-inline size_t z_smem_bytes(int K)
-{
-    return sizeof(double) * (size_t)(kZRows * K + K * 33) + sizeof(int) * (size_t)(K * kZThreads + kZRows * kZCols);
-}
+// per warp: E_w [K][33] f64, cum [K][32] f64, P_w [4][K] f64, znj [K][32] i32, zc [K][32] u8
+inline size_t z_smem_bytes_per_warp(int K) { return (size_t)K * (8 * (33 + 32 + kZUnitRows) + 4 * 32 + 32); }
 
-__global__ void __launch_bounds__(kZThreads) z_alloc_fused(const ZParams p)
+__global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *m_s = reinterpret_cast<int *>(smem_raw);                                   // [32][32], 16-byte aligned for int4
-    double *P_s = reinterpret_cast<double *>(smem_raw + sizeof(int) * kZRows * kZCols);   // [32][K]
-    double *E_s = P_s + kZRows * p.K;                            // [K][33]
-    int *znj_s = reinterpret_cast<int *>(E_s + p.K * 33);        // [K][128]
-    __shared__ int tile_sh;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int I = p.I, J = p.J, K = p.K;
+    unsigned char *base = smem_raw + (size_t)warp * p.warp_smem;
+    double *E_w = reinterpret_cast<double *>(base);
+    double *cum = E_w + K * 33;
+    double *P_w = cum + K * 32;
+    int *znj = reinterpret_cast<int *>(P_w + kZUnitRows * K);
+    unsigned char *zc = reinterpret_cast<unsigned char *>(znj + K * 32);
 
     // zero the other half of the ping-pong for the next launch
     {
-        const size_t gtid = (size_t)blockIdx.x * kZThreads + tid, gsz = (size_t)gridDim.x * kZThreads;
+        const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
         for (size_t i = gtid; i < (size_t)I * K; i += gsz) p.Zin_next[i] = 0;
         for (size_t i = gtid; i < (size_t)K * J; i += gsz) p.Znj_next[i] = 0;
     }
+    for (int k = 0; k < K; ++k) zc[k * 32 + lane] = 0;      // invariant: all zero between cells
+    int pow2 = 0;                                           // largest power of two <= K-1
+    if (K > 1) { pow2 = 1; while (pow2 * 2 <= K - 1) pow2 *= 2; }
 
     for (;;) {
-        if (tid == 0) tile_sh = (int)(atomicAdd(p.tile_counter, 1ULL) - p.tile_base);
-        __syncthreads();
-        const int tile = tile_sh;
-        if (tile >= p.n_tiles) break;
-        const int ct = tile / p.n_rb, rb = tile - ct * p.n_rb;
-        const int j0 = ct * kZCols, i0 = rb * kZRows;
+        int unit = 0;
+        if (lane == 0) unit = (int)(atomicAdd(p.unit_counter, 1ULL) - p.unit_base);
+        unit = __shfl_sync(kFull, unit, 0);
+        if (unit >= p.n_units) break;
+        const int ct = unit / p.n_rc, rc = unit - ct * p.n_rc;
+        const int j0 = ct * 32, i0 = rc * kZUnitRows;
+        const int jo = p.col_id[j0 + lane];
+        // stage E[., 32 genomes] (gather by original genome), P[4 rows, .]; clear the unit's Znj
+        {
+            int k = lane, jl = 0;
+            while (k >= K) { k -= K; ++jl; }
+            for (int idx = lane; idx < K * 32; idx += 32) {
+                const int js = __shfl_sync(kFull, jo, jl);
+                E_w[k * 33 + jl] = (js >= 0) ? p.E[(size_t)K * js + k] : 0.0;
+                k += 32;
+                while (k >= K) { k -= K; ++jl; }
+            }
+        }
+        for (int idx = lane; idx < kZUnitRows * K; idx += 32) {
+            const int r = idx & (kZUnitRows - 1), k = idx / kZUnitRows;
+            P_w[r * K + k] = (i0 + r < I) ? p.P[(size_t)(i0 + r) + (size_t)I * k] : 0.0;
+        }
+        for (int k = 0; k < K; ++k) znj[k * 32 + lane] = 0;
+        __syncwarp();
 
-        for (int idx = tid; idx < kZRows * K; idx += kZThreads) {
-            const int rl = idx & 31, k = idx >> 5;
-            P_s[rl * K + k] = (i0 + rl < I) ? p.P[(size_t)(i0 + rl) + (size_t)I * k] : 0.0;
-        }
-        for (int idx = tid; idx < K * kZCols; idx += kZThreads) {
-            const int jl = idx / K, k = idx - jl * K;
-            E_s[k * 33 + jl] = (j0 + jl < J) ? p.E[(size_t)K * j0 + idx] : 0.0;
-        }
-        for (int idx = tid; idx < kZRows * (kZCols / 4); idx += kZThreads) {
-            const int row = idx >> 3, c4 = idx & 7;
-            int4 v = make_int4(0, 0, 0, 0);
-            if (i0 + row < I) v = *reinterpret_cast<const int4 *>(p.M + (size_t)(i0 + row) * p.Jp + j0 + 4 * c4);
-            *reinterpret_cast<int4 *>(m_s + row * kZCols + 4 * c4) = v;
-        }
-        for (int idx = tid; idx < K * kZThreads; idx += kZThreads) znj_s[idx] = 0;
-        __syncthreads();
-
-        const int j = j0 + lane;
-        for (int r = 0; r < 8; ++r) {
-            const int rl = warp * 8 + r, row = i0 + rl;
-            const int n = m_s[rl * kZCols + lane];
+        for (int r = 0; r < kZUnitRows; ++r) {
+            const int row = i0 + r;
+            if (row >= I) break;
+            const int n = (jo >= 0) ? p.M[(size_t)row * p.Jp + j0 + lane] : 0;
             if (!__any_sync(kFull, n > 0)) continue;
-            const double *Pr = P_s + rl * K;
-            double S = 0.0;
-            for (int k = 0; k < K; ++k) S = fma(Pr[k], E_s[k * 33 + lane], S);
-            const bool degenerate = !(S > 0.0 && S <= 1.7976931348623157e308);
-            int nrem = (n > 0 && !degenerate) ? n : 0;
-            const int nlast = (n > 0 && degenerate) ? n : 0;
+            const double *Pr = P_w + r * K;
+            const bool maybe_small = __any_sync(kFull, n > 0 && n <= kNDirect);
+            double S = 0.0, c = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double pe = Pr[k], ee = E_w[k * 33 + lane];
+                S = fma(pe, ee, S);
+                if (maybe_small) { c = c + pe * ee; cum[k * 32 + lane] = c; }
+            }
+            const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
+            const bool small = n > 0 && ok && n <= kNDirect;
+            int nrem = (n > kNDirect && ok) ? n : 0;
+            const int nlast = (n > 0 && !ok) ? n : 0;       // degenerate probabilities: all to the last class
             UStream us;
-            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * j));
-            double rem = S;
-            for (int k = 0; k <= K - 1; ++k) {
-                int z = 0;
-                if (k < K - 1) {
-                    if (!__any_sync(kFull, nrem > 0)) { k = K - 2; continue; }   // jump to the remainder class
-                    if (nrem > 0) {
-                        const double prob = Pr[k] * E_s[k * 33 + lane];
-                        if (prob != 0.0) {
-                            const double pp = prob / rem;
-                            z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, nrem, pp) : nrem;
-                            nrem -= z;
+            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * jo));
+
+            // ---- direct method for the small counts of this row
+            if (__any_sync(kFull, small)) {
+                const int tmax = __reduce_max_sync(kFull, small ? n : 0);
+                unsigned touched = 0;
+                double ua = 0.0, ub = 0.0;
+                for (int t = 0; t < tmax; ++t) {
+                    if ((t & 1) == 0) us.pair((uint32_t)t >> 1, ua, ub);      // converged: once per two draws
+                    if (small && t < n) {
+                        const double x = ((t & 1) ? ub : ua) * S;
+                        int pos = 0;                                          // number of thresholds <= x
+                        for (int step = pow2; step; step >>= 1) {
+                            const int np = pos + step;
+                            if (np <= K - 1 && cum[(np - 1) * 32 + lane] <= x) pos = np;
                         }
-                        rem = rem - prob;
+                        zc[pos * 32 + lane] += 1;
+                        touched |= 1u << (pos & 31);
                     }
-                } else {
-                    z = nrem + nlast;
                 }
-                const int zs = __reduce_add_sync(kFull, z);
-                if (zs) {
-                    if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
-                    if (z) {
-                        znj_s[k * kZThreads + tid] += z;
-                        if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)j + (size_t)J * k)] = (double)z;
+                unsigned todo = (K <= 32) ? __reduce_or_sync(kFull, touched) : 0xffffffffu;
+                for (int k = 0; k < K; ++k) {
+                    if (K <= 32 && !((todo >> k) & 1u)) continue;
+                    const int z = zc[k * 32 + lane];
+                    const int zs = __reduce_add_sync(kFull, z);
+                    if (zs) {
+                        if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
+                        if (z) {
+                            zc[k * 32 + lane] = 0;
+                            znj[k * 32 + lane] += z;
+                            if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)jo + (size_t)J * k)] = (double)z;
+                        }
+                    }
+                }
+            }
+
+            // ---- conditional-binomial chain for the large counts (and the degenerate cells)
+            if (__any_sync(kFull, (nrem | nlast) != 0)) {
+                double rem = S, u_even = 0.0, u_odd = 0.0;
+                for (int k = 0; k <= K - 1; ++k) {
+                    int z = 0;
+                    if (k < K - 1) {
+                        if (!__any_sync(kFull, nrem > 0)) { k = K - 2; continue; }   // jump to the remainder class
+                        if ((k & 1) == 0) us.pair((uint32_t)k >> 1, u_even, u_odd); // converged: once per two classes
+                        if (nrem > 0) {
+                            const double prob = Pr[k] * E_w[k * 33 + lane];
+                            if (prob != 0.0) {
+                                const double pp = prob / rem;
+                                z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, k, (k & 1) ? u_odd : u_even, nrem, pp) : nrem;
+                                nrem -= z;
+                            }
+                            rem = rem - prob;
+                        }
+                    } else {
+                        z = nrem + nlast;
+                    }
+                    const int zs = __reduce_add_sync(kFull, z);
+                    if (zs) {
+                        if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
+                        if (z) {
+                            znj[k * 32 + lane] += z;
+                            if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)jo + (size_t)J * k)] = (double)z;
+                        }
                     }
                 }
             }
         }
-        __syncthreads();
-        for (int idx = tid; idx < K * kZCols; idx += kZThreads) {
-            const int k = idx >> 5, jl = idx & 31;
-            const int *zp = znj_s + k * kZThreads + jl;
-            const int s = zp[0] + zp[32] + zp[64] + zp[96];
-            if (s) atomicAdd(p.Znj + (size_t)k + (size_t)K * (j0 + jl), s);
-        }
-        __syncthreads();
+        if (jo >= 0)
+            for (int k = 0; k < K; ++k) {
+                const int s = znj[k * 32 + lane];
+                if (s) atomicAdd(p.Znj + (size_t)k + (size_t)K * jo, s);
+            }
+        __syncwarp();
     }
 }
 
@@ -434,12 +499,14 @@ __global__ void test_math(int fn, const double *x, double *y, int n)
     const double v = x[i];
     y[i] = fn == 0 ? det_log(v) : fn == 1 ? det_exp(v) : fn == 2 ? det_lgamma(v) : det_ppnd16(v);
 }
-__global__ void test_binomial(Key key, uint32_t sweep, uint32_t stream, const int *n, const double *pp, int *out, int count)
+__global__ void test_binomial(Key key, uint32_t sweep, uint32_t stream, int kstep, const int *n, const double *pp, int *out, int count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     UStream us; us.init(key, sweep, stream, (uint32_t)i);
-    out[i] = binomial_draw(us, n[i], pp[i]);
+    double u0, u1;
+    us.pair((uint32_t)kstep >> 1, u0, u1);
+    out[i] = binomial_draw(us, kstep, (kstep & 1) ? u1 : u0, n[i], pp[i]);
 }
 __global__ void test_gamma(Key key, uint32_t sweep, uint32_t stream, const double *shape, const double *rate, double *out, int count)
 {

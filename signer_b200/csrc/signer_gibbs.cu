@@ -48,13 +48,15 @@ constexpr size_t kRingBytes = size_t(3) << 30;   // per ring set (two sets)
 // The data of one cohort on one device, shared by every chain on that device.
 struct DeviceData {
     int device = 0, I = 0, J = 0, Jp = 0, n2 = 0;
-    int *M = nullptr;          // [I][Jp]
+    int *M = nullptr;          // [I][Jp], columns in z_alloc's burden order
+    int *col_id = nullptr;     // [Jp] original genome of each position of M (-1: padding)
+    int *Mrow = nullptr;       // [I][Jp], original genome order (log-likelihood)
     double *W = nullptr;       // [I][Jp]
     double *lgm = nullptr;     // sum lgamma(M+1), one double
     ~DeviceData()
     {
         cudaSetDevice(device);
-        cudaFree(M); cudaFree(W); cudaFree(lgm);
+        cudaFree(M); cudaFree(Mrow); cudaFree(col_id); cudaFree(W); cudaFree(lgm);
     }
 };
 
@@ -67,8 +69,9 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
     d->device = device; d->I = I; d->J = J; d->Jp = (J + 31) / 32 * 32;
     d->n2 = 1; while (d->n2 < J) d->n2 <<= 1;
     const size_t n = (size_t)I * d->Jp;
-    std::vector<int> m(n, 0);
+    std::vector<int> m(n, 0), msort(n, 0);
     std::vector<double> w(n, 0.0);
+    std::vector<long long> burden(J, 0);
     for (int j = 0; j < J; ++j)
         for (int i = 0; i < I; ++i) {
             const double mv = M[(size_t)i + (size_t)I * j], wv = W[(size_t)i + (size_t)I * j];
@@ -76,17 +79,30 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
             if (!(wv >= 0.0) || !(wv <= 1.7976931348623157e308)) return fail(SIGNER_ERR_NONFINITE, "W has a negative or non-finite entry");
             m[(size_t)i * d->Jp + j] = (int)mv;          // int size (src/gibbs_2.cpp:31)
             w[(size_t)i * d->Jp + j] = wv;
+            burden[j] += (long long)(int)mv;
         }
+    // z_alloc_fused visits the genomes in order of decreasing burden (a private order: results do not depend on it)
+    std::vector<int> order(J), col_id(d->Jp, -1);
+    for (int j = 0; j < J; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return burden[a] > burden[b]; });
+    for (int pos = 0; pos < J; ++pos) {
+        col_id[pos] = order[pos];
+        for (int i = 0; i < I; ++i) msort[(size_t)i * d->Jp + pos] = m[(size_t)i * d->Jp + order[pos]];
+    }
     CU(cudaMalloc(&d->M, n * sizeof(int)));
+    CU(cudaMalloc(&d->Mrow, n * sizeof(int)));
+    CU(cudaMalloc(&d->col_id, (size_t)d->Jp * sizeof(int)));
     CU(cudaMalloc(&d->W, n * sizeof(double)));
     CU(cudaMalloc(&d->lgm, sizeof(double)));
-    CU(cudaMemcpy(d->M, m.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->M, msort.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->Mrow, m.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->col_id, col_id.data(), (size_t)d->Jp * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d->W, w.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     // constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180)
     double *col = nullptr;
     CU(cudaMalloc(&col, (size_t)d->n2 * sizeof(double)));
     CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
-    LLParams lp{I, J, d->Jp, 1, d->M, d->W, nullptr, nullptr, col, 1};
+    LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1};
     const int nchunk = (I + kLLChunk - 1) / kLLChunk;
     const size_t smem = sizeof(double) * (size_t)(33 + nchunk * 32);
     loglik_cols<<<(J + 31) / 32, 128, smem>>>(lp);
@@ -120,7 +136,7 @@ struct signer_chain {
     double *stats = nullptr;
     unsigned long long *tile_counter = nullptr;
     unsigned long long z_launches = 0;
-    int z_grid = 0, n_rb = 0, n_tiles = 0;
+    int z_grid = 0, n_rc = 0, n_units = 0, z_warp_smem = 0;
     int kg_per_split = 2, ksplit = 1;
     Hyper h{};
     Key key{};
@@ -194,18 +210,18 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     const int tgt = c->zcur ^ 1;
     ZParams p{};
     p.I = c->I; p.J = c->J; p.Jp = c->Jp; p.K = c->K;
-    p.M = c->data->M; p.P = c->P; p.E = c->E;
+    p.M = c->data->M; p.col_id = c->data->col_id; p.P = c->P; p.E = c->E;
     p.Zin = c->Zin[tgt]; p.Znj = c->Znj[tgt];
     p.Zin_next = c->Zin[c->zcur]; p.Znj_next = c->Znj[c->zcur];
     p.Zcube = zcube;
-    p.tile_counter = c->tile_counter;
-    p.tile_base = c->z_launches * (unsigned long long)(c->n_tiles + c->z_grid);
-    p.n_rb = c->n_rb; p.n_tiles = c->n_tiles;
+    p.unit_counter = c->tile_counter;
+    p.unit_base = c->z_launches * (unsigned long long)(c->n_units + c->z_grid * kZWarps);   // every warp overshoots once
+    p.n_rc = c->n_rc; p.n_units = c->n_units; p.warp_smem = c->z_warp_smem;
     p.key = c->key; p.sweep = sweep; p.stream = stream_id;
     if (zcube) CU(cudaMemsetAsync(zcube, 0, sizeof(double) * (size_t)c->I * c->J * c->K, c->stream));
     {
         ProfScope ps(c, 0);
-        z_alloc_fused<<<c->z_grid, kZThreads, z_smem_bytes(c->K), c->stream>>>(p);
+        z_alloc_fused<<<c->z_grid, 32 * kZWarps, (size_t)c->z_warp_smem * kZWarps, c->stream>>>(p);
     }
     CU(cudaGetLastError());
     c->z_launches++;
@@ -250,7 +266,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
 
 int launch_loglik(signer_chain *c, double *out)
 {
-    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->M, c->data->W, c->P, c->E, c->col, 0};
+    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col, 0};
     const int nchunk = (c->I + kLLChunk - 1) / kLLChunk;
     const size_t smem = sizeof(double) * (size_t)(c->K * 33 + nchunk * 32);
     {
@@ -411,15 +427,16 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     CU(cudaMalloc(&c->stats, 8 * sizeof(double)));
 
     // launch geometry
-    c->n_rb = (c->I + kZRows - 1) / kZRows;
-    c->n_tiles = c->n_rb * (c->Jp / kZCols);
-    const size_t zsm = z_smem_bytes(K);
+    c->n_rc = (c->I + kZUnitRows - 1) / kZUnitRows;
+    c->n_units = c->n_rc * (c->Jp / 32);
+    c->z_warp_smem = (int)z_smem_bytes_per_warp(K);
+    const size_t zsm = (size_t)c->z_warp_smem * kZWarps;
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
     int occ = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, kZThreads, zsm));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * kZWarps, zsm));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     if (occ < 1) return fail(SIGNER_ERR_ARG, "z_alloc_fused does not fit on an SM for this K");
-    c->z_grid = std::max(1, std::min(c->n_tiles, occ * sms));
+    c->z_grid = std::max(1, std::min((c->n_units + kZWarps - 1) / kZWarps, occ * sms));
     const int nkg = (K + 3) / 4;
     c->kg_per_split = 2;
     c->ksplit = (nkg + c->kg_per_split - 1) / c->kg_per_split;
@@ -708,8 +725,8 @@ int signer_test_math(int32_t fn, const double *x, double *y, int32_t n, int32_t 
     return SIGNER_OK;
 }
 
-int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, const int32_t *n, const double *p, int32_t *out,
-                         int32_t count, int32_t device)
+int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, int32_t kstep, const int32_t *n, const double *p,
+                         int32_t *out, int32_t count, int32_t device)
 {
     g_err.clear();
     if (!n || !p || !out || count < 0) return fail(SIGNER_ERR_ARG, "bad argument");
@@ -719,7 +736,7 @@ int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, cons
     CU(cudaMalloc(&dn, 4 * c)); CU(cudaMalloc(&dout, 4 * c)); CU(cudaMalloc(&dp, 8 * c));
     CU(cudaMemcpy(dn, n, 4 * (size_t)count, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dp, p, 8 * (size_t)count, cudaMemcpyHostToDevice));
-    if (count) test_binomial<<<(count + 127) / 128, 128>>>(Key{(uint32_t)seed, (uint32_t)(seed >> 32)}, sweep, stream_id, dn, dp, dout, count);
+    if (count) test_binomial<<<(count + 127) / 128, 128>>>(Key{(uint32_t)seed, (uint32_t)(seed >> 32)}, sweep, stream_id, kstep, dn, dp, dout, count);
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, dout, 4 * (size_t)count, cudaMemcpyDeviceToHost));
     cudaFree(dn); cudaFree(dout); cudaFree(dp);

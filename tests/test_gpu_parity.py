@@ -45,11 +45,12 @@ def test_binomial_bit_exact(sg, oracle):
     n = np.concatenate([rng.integers(1, 60, 20000), rng.integers(1, 30000, 20000), [1, 1, 2, 2147483647 // 4]]).astype(np.int32)
     p = np.concatenate([10 ** rng.uniform(-9, 0, 20000), rng.uniform(0, 1, 20000), [0.5, 1e-300, 0.999999, 1e-7]])
     p = np.clip(p, 1e-300, 1 - 1e-16)
-    out = np.zeros(n.size, dtype=np.int32)
-    _lib.check(_lib.lib().signer_test_binomial(11, 3, 1, n.ctypes.data_as(_lib.ip), _dp(p), out.ctypes.data_as(_lib.ip), n.size, 0))
     L = oracle.lib()
-    want = np.array([L.oracle_binomial(11, 3, 1, e, int(n[e]), float(p[e])) for e in range(n.size)])
-    assert np.array_equal(out, want)
+    for kstep in (0, 1, 6, 127):
+        out = np.zeros(n.size, dtype=np.int32)
+        _lib.check(_lib.lib().signer_test_binomial(11, 3, 1, kstep, n.ctypes.data_as(_lib.ip), _dp(p), out.ctypes.data_as(_lib.ip), n.size, 0))
+        want = np.array([L.oracle_binomial(11, 3, 1, e, kstep, int(n[e]), float(p[e])) for e in range(n.size)])
+        assert np.array_equal(out, want)
     assert (out >= 0).all() and (out <= n).all()
 
 
