@@ -33,14 +33,15 @@
  *   stream ids: 0 permutation, 1..7 Gibbs steps, 8 initial Z
  *   element: step 1/8: i + I*j ; P family (2,4,6): i + I*k ; E family (3,5,7): k + K*j
  *   u53(w0,w1) = (2*((w0>>6)<<26 | (w1>>6)) + 1) * 2^-53       in (0,1)
- *   step 1, cells with count n <= 16: direct method, n categorical draws; draw t uses half (t&1) of
- *                block (t>>1): x = u*S, class = first k < K-1 with x < c_k, c_k = c_{k-1} + P[i,k]*E[k,j],
+ *   u32(w) = (w + 1/2) * 2^-32: step-1 uniforms carry 32 random bits like R's unif_rand (Mersenne-Twister)
+ *   step 1, cells with count n <= 16: direct method, n categorical draws; draw t uses word (t&3) of
+ *                block (t>>2): x = u*S, class = first k < K-1 with x < c_k, c_k = c_{k-1} + P[i,k]*E[k,j],
  *                else the last class.  Larger cells: sequential conditional binomials (rmultinom):
- *   step 1, conditional binomial of class k: the inversion uniform is half (k&1) of block (k>>1);
- *                BTRS attempt t of class k reads block 0x1000 + (k<<8) + t (U from the first half, V second)
+ *   step 1, conditional binomial of class k: the inversion uniform is word (k&3) of block (k>>2);
+ *                BTRS attempt t of class k reads block 0x1000 + (k<<8) + t (U from word 0, V from word 1)
  *   gamma draws: Marsaglia-Tsang attempt t uses block t: x = ppnd16(u(w0,w1)), accept test u(w2,w3);
  *                block 0xFFFFFFFF gives (boost uniform for shape<1, MH acceptance uniform)
- *   binomial(n,pp): p=min(pp,1-pp); n*p<10 -> inversion from q^n (binary powering), recurrence
+ *   binomial(n,pp): p=min(pp,1-pp); n*p<30 -> inversion from q^n (binary powering), recurrence
  *                   r <- (r * (s*(n-x+1))) * (1/x); else Hormann BTRS; flip back if pp>0.5
  *   fp reductions: PE = fma chain over k; corrP = fma chain over i; corrE = 128-column segment
  *                  fma chains, segments added in ascending order (per shard, shards ascending);
@@ -54,7 +55,7 @@
 
 #define ORACLE_SEG 128
 #define ORACLE_LLCHUNK 32
-#define BINV_MAX 10.0
+#define BINV_MAX 30.0
 #define TINY 1e-160
 #define AUX_BLOCK 0xFFFFFFFFu
 #define BTRS_BLOCK0 0x1000u
@@ -88,6 +89,10 @@ double oracle_u53(uint32_t w0, uint32_t w1)
     return (double)(2 * x + 1) * 0x1p-53;
 }
 
+/* 32-bit uniform (w + 1/2) * 2^-32 in (0,1): the resolution of R's own unif_rand() under its
+ * default generator (Mersenne-Twister, 32 random bits per uniform), used by every step-1 draw. */
+double oracle_u32(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
+
 typedef struct {
     uint32_t key[2];
     uint32_t elem, stream, sweep;
@@ -97,6 +102,13 @@ static void us_init(ustream *s, uint64_t seed, uint32_t sweep, uint32_t stream, 
 {
     s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
     s->elem = elem; s->stream = stream; s->sweep = sweep;
+}
+
+static void us_quad(const ustream *s, uint32_t block, double u[4])
+{
+    uint32_t ctr[4] = { block, s->elem, s->stream, s->sweep }, w[4];
+    oracle_philox(ctr, s->key, w);
+    for (int i = 0; i < 4; i++) u[i] = oracle_u32(w[i]);
 }
 
 static void us_block(const ustream *s, uint32_t block, double *u0, double *u1)
@@ -247,8 +259,8 @@ static double btrs_fc(double k)
         0.01664469118982119, 0.01387612882307075, 0.01189670994589177, 0.01041126526197209,
         0.009255462182712733, 0.008330563433362871 };
     if (k <= 9.0) return tab[(int)k];
-    double kp1 = k + 1.0, sq = kp1 * kp1;
-    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / sq) / sq) / kp1;
+    double ri = 1.0 / (k + 1.0), ri2 = ri * ri;
+    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0) * ri2) * ri2) * ri;
 }
 
 /* Binomial(n, pp), n >= 1, 0 < pp < 1.  Small n*p: sequential-search inversion ("BINV",
@@ -270,9 +282,9 @@ static int binomial_draw(const ustream *s, int kstep, int n, double pp)
             if (!e) break;
             b = b * b;
         }
-        double u0, u1;
-        us_block(s, (uint32_t)kstep >> 1, &u0, &u1);
-        double u = (kstep & 1) ? u1 : u0;
+        double uq[4];
+        us_quad(s, (uint32_t)kstep >> 2, uq);
+        double u = uq[kstep & 3];
         x = 0;
         if (u >= r) {
             double sr = p / q;
@@ -295,9 +307,9 @@ static int binomial_draw(const ustream *s, int kstep, int n, double pp)
         double kd = 0.0;
         x = -1;
         for (uint32_t t = 0; t < 256; t++) {
-            double U, V;
-            us_block(s, BTRS_BLOCK0 + ((uint32_t)kstep << 8) + t, &U, &V);
-            U = U - 0.5;
+            double uq[4];
+            us_quad(s, BTRS_BLOCK0 + ((uint32_t)kstep << 8) + t, uq);
+            double U = uq[0] - 0.5, V = uq[1];
             double us = 0.5 - fabs(U);
             kd = floor((2.0 * a / us + b) * U + c);
             if (us >= 0.07 && V <= vr) { x = (int)kd; break; }
@@ -409,9 +421,9 @@ static void multinomial_cell(uint64_t seed, uint32_t sweep, uint32_t stream, int
         /* per-count algorithm switch: small counts use the direct method -- n categorical draws,
          * draw t from half (t&1) of block (t>>1): class = first k with u*S < cumulative sum */
         for (int t = 0; t < n; t++) {
-            double u0, u1;
-            us_block(&us, (uint32_t)t >> 1, &u0, &u1);
-            double x = ((t & 1) ? u1 : u0) * S;
+            double uq[4];
+            us_quad(&us, (uint32_t)t >> 2, uq);
+            double x = uq[t & 3] * S;
             double c = 0.0;
             int cls = K - 1;
             for (int m = 0; m < K - 1; m++) {

@@ -1,4 +1,4 @@
-// draws.cuh -- device primitives of the draw specification v2.
+// draws.cuh -- device primitives of the draw specification v4.
 //
 // Everything here is built from IEEE-754 correctly rounded fp64 operations (+ - * / sqrt fma) in
 // a fixed order, plus integer arithmetic, so that results are bit-identical to any other
@@ -18,7 +18,7 @@ namespace sg {
 #define SG_D __device__ __forceinline__
 
 constexpr double kTiny = 1e-160;              // pow(10,-160) clamps, src/gibbs_2.cpp:40-41,150,166,182,223
-constexpr double kBinvMax = 10.0;             // n*p below this: inversion; otherwise BTRS
+constexpr double kBinvMax = 30.0;             // n*p below this: inversion (as R's rbinom); otherwise BTRS
 constexpr uint32_t kAuxBlock = 0xFFFFFFFFu;   // block holding (boost uniform, MH uniform)
 constexpr uint32_t kBtrsBlock0 = 0x1000u;     // first BTRS block of a step-1 stream
 constexpr int kSeg = 128;                     // columns per corrE segment
@@ -55,6 +55,13 @@ SG_D double u53(uint32_t w0, uint32_t w1)
     return (__hiloint2double((int)hi, (int)lo) - 1.0) + 0x1p-53;
 }
 
+// (w + 1/2) * 2^-32 in (0,1): 32 random bits, the resolution of R's unif_rand (Mersenne-Twister).
+// 1.(w << 20) - 1 = w * 2^-32 exactly; adding 2^-33 is exact (33 significant bits).
+SG_D double u32(uint32_t w)
+{
+    return (__hiloint2double((int)(0x3ff00000u | (w >> 12)), (int)(w << 20)) - 1.0) + 0x1p-33;
+}
+
 struct Key { uint32_t k0, k1; };
 
 // A stream is addressed by (key, sweep, stream id, element); its blocks are addressed directly.
@@ -70,6 +77,7 @@ struct UStream {
         u0 = u53(w.x, w.y);
         u1 = u53(w.z, w.w);
     }
+    SG_D U4 words(uint32_t b) const { return philox4x32_10(b, elem, stream, sweep, k0, k1); }
 };
 
 // ---------------------------------------------------------------- deterministic elementary functions
@@ -206,8 +214,8 @@ __constant__ double c_btrs_fc[10] = {
 SG_D double btrs_fc(double k)
 {
     if (k <= 9.0) return c_btrs_fc[(int)k];
-    const double kp1 = k + 1.0, sq = kp1 * kp1;
-    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / sq) / sq) / kp1;
+    const double ri = 1.0 / (k + 1.0), ri2 = ri * ri;
+    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0) * ri2) * ri2) * ri;
 }
 
 // 1/x for x = 1..255 (entry 0 unused): the inversion recurrence multiplies by the correctly
@@ -220,10 +228,40 @@ __device__ const RcpTab g_rcp_tab = RcpTab();
 
 SG_D double rcp_int(int x, double xd) { return x < 256 ? __ldg(&g_rcp_tab.v[x]) : 1.0 / xd; }
 
+// Hormann's BTRS (transformed rejection with squeeze) for n*p >= kBinvMax, p <= 1/2.  Out of line:
+// it is rare and register-hungry.  Attempt t reads block kBtrsBlock0 + (kstep<<8) + t.
+__device__ __noinline__ int btrs_draw(UStream s, int kstep, int n, double p)
+{
+    const double q = 1.0 - p, nd = (double)n;
+    const double spq = sqrt(nd * p * q);
+    const double b = 1.15 + 2.53 * spq;
+    const double a = -0.0873 + 0.0248 * b + 0.01 * p;
+    const double c = nd * p + 0.5;
+    const double vr = 0.92 - 4.2 / b;
+    const double alpha = (2.83 + 5.1 / b) * spq;
+    const double r = p / q;
+    const double m = floor((nd + 1.0) * p);
+    double kd = 0.0;
+    for (uint32_t t = 0; t < 256; ++t) {
+        const U4 w = s.words(kBtrsBlock0 + ((uint32_t)kstep << 8) + t);
+        const double U = u32(w.x) - 0.5, V = u32(w.y);
+        const double us = 0.5 - fabs(U);
+        kd = floor((2.0 * a / us + b) * U + c);
+        if (us >= 0.07 && V <= vr) return (int)kd;
+        if (kd < 0.0 || kd > nd) continue;
+        const double lv = det_log(V * alpha / (a / (us * us) + b));
+        const double ub = (m + 0.5) * det_log((m + 1.0) / (r * (nd - m + 1.0)))
+                        + (nd + 1.0) * det_log((nd - m + 1.0) / (nd - kd + 1.0))
+                        + (kd + 0.5) * det_log(r * (nd - kd + 1.0) / (kd + 1.0))
+                        + btrs_fc(m) + btrs_fc(nd - m) - btrs_fc(kd) - btrs_fc(nd - kd);
+        if (lv <= ub) return (int)kd;
+    }
+    return (kd < 0.0) ? 0 : (kd > nd) ? n : (int)kd;
+}
+
 // Binomial(n, pp) for n >= 1, 0 < pp < 1, conditional binomial number `kstep` of its cell.
-// u_binv: the inversion uniform = half (kstep&1) of block (kstep>>1) of the cell's stream (the
-// caller generates it, warp-converged, once per two steps).  BTRS attempt t reads block
-// kBtrsBlock0 + (kstep<<8) + t of the same stream.
+// u_binv: the inversion uniform = u32(word (kstep&3) of block (kstep>>2)) of the cell's stream (the
+// caller generates the block, warp-converged, once per four steps).
 SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double pp)
 {
     const bool flip = pp > 0.5;
@@ -252,33 +290,7 @@ SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double
             }
         }
     } else {
-        // Hormann's BTRS: transformed rejection with squeeze
-        const double spq = sqrt(nd * p * q);
-        const double b = 1.15 + 2.53 * spq;
-        const double a = -0.0873 + 0.0248 * b + 0.01 * p;
-        const double c = nd * p + 0.5;
-        const double vr = 0.92 - 4.2 / b;
-        const double alpha = (2.83 + 5.1 / b) * spq;
-        const double r = p / q;
-        const double m = floor((nd + 1.0) * p);
-        double kd = 0.0;
-        x = -1;
-        for (uint32_t t = 0; t < 256; ++t) {
-            double U, V;
-            s.pair(kBtrsBlock0 + ((uint32_t)kstep << 8) + t, U, V);
-            U = U - 0.5;
-            const double us = 0.5 - fabs(U);
-            kd = floor((2.0 * a / us + b) * U + c);
-            if (us >= 0.07 && V <= vr) { x = (int)kd; break; }
-            if (kd < 0.0 || kd > nd) continue;
-            const double lv = det_log(V * alpha / (a / (us * us) + b));
-            const double ub = (m + 0.5) * det_log((m + 1.0) / (r * (nd - m + 1.0)))
-                            + (nd + 1.0) * det_log((nd - m + 1.0) / (nd - kd + 1.0))
-                            + (kd + 0.5) * det_log(r * (nd - kd + 1.0) / (kd + 1.0))
-                            + btrs_fc(m) + btrs_fc(nd - m) - btrs_fc(kd) - btrs_fc(nd - kd);
-            if (lv <= ub) { x = (int)kd; break; }
-        }
-        if (x < 0) x = (kd < 0.0) ? 0 : (kd > nd) ? n : (int)kd;
+        x = btrs_draw(s, kstep, n, p);
     }
     return flip ? n - x : x;
 }

@@ -34,11 +34,11 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 // global counter).  Per row the 32 lanes draw their cells' allocations with the per-count switch
 // of the draw specification:
 //   n <= 16 : direct method -- n categorical draws by binary search in the lane's cumulative
-//             P[i,.] o E[.,j]; the Philox block of draws (t, t+1) is generated warp-converged;
+//             P[i,.] o E[.,j]; the Philox block of four draws is generated warp-converged;
 //   n  > 16 : R's rmultinom structure -- the K classes in lockstep, one conditional binomial each.
 // The class counts are reduced on the spot: over the 32 genomes with one REDUX (-> Zin, one
-// integer atomic per row/class/warp) and per lane over the unit's rows (-> Znj, shared memory,
-// one atomic per class/genome/unit).  Z itself is never written (except, on request, the final
+// integer atomic per row/class/warp); the per-genome sums Znj take one integer atomic per non-zero
+// count (fire-and-forget reductions into L2).  Z itself is never written (except, on request, the final
 // sweep's cube for the reference's `Zs`).
 //
 // Genomes are visited in a kernel-private order, sorted by mutation burden (col_id maps a
@@ -66,20 +66,24 @@ struct ZParams {
     uint32_t sweep, stream;
 };
 
-// per warp: E_w [K][33] f64, cum [K][32] f64, P_w [4][K] f64, znj [K][32] i32, zc [K][32] u8
-inline size_t z_smem_bytes_per_warp(int K) { return (size_t)K * (8 * (33 + 32 + kZUnitRows) + 4 * 32 + 32); }
+// per warp: E_w [K][33] f64, cum4 [ceil((K-1)/4)][32] f64, P_w [4][K] f64, zc [K][32] u8
+inline int z_groups(int K) { return (K - 1 + 3) / 4; }
+inline size_t z_smem_bytes_per_warp(int K)
+{
+    return (size_t)8 * ((size_t)K * 33 + (size_t)z_groups(K) * 32 + (size_t)kZUnitRows * K) + ((size_t)K * 32 + 7) / 8 * 8;
+}
 
-__global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p)
+__global__ void __launch_bounds__(32 * kZWarps, 12) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int I = p.I, J = p.J, K = p.K;
     unsigned char *base = smem_raw + (size_t)warp * p.warp_smem;
     double *E_w = reinterpret_cast<double *>(base);
-    double *cum = E_w + K * 33;
-    double *P_w = cum + K * 32;
-    int *znj = reinterpret_cast<int *>(P_w + kZUnitRows * K);
-    unsigned char *zc = reinterpret_cast<unsigned char *>(znj + K * 32);
+    const int ng = (K - 1 + 3) / 4;                         // groups of four thresholds
+    double *cum4 = E_w + K * 33;                            // cumulative P o E at the end of each group
+    double *P_w = cum4 + ng * 32;
+    unsigned char *zc = reinterpret_cast<unsigned char *>(P_w + kZUnitRows * K);
 
     // zero the other half of the ping-pong for the next launch
     {
@@ -88,8 +92,8 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
         for (size_t i = gtid; i < (size_t)K * J; i += gsz) p.Znj_next[i] = 0;
     }
     for (int k = 0; k < K; ++k) zc[k * 32 + lane] = 0;      // invariant: all zero between cells
-    int pow2 = 0;                                           // largest power of two <= K-1
-    if (K > 1) { pow2 = 1; while (pow2 * 2 <= K - 1) pow2 *= 2; }
+    int pow2 = 0;                                           // largest power of two <= ng
+    if (ng > 0) { pow2 = 1; while (pow2 * 2 <= ng) pow2 *= 2; }
 
     for (;;) {
         int unit = 0;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
         const int ct = unit / p.n_rc, rc = unit - ct * p.n_rc;
         const int j0 = ct * 32, i0 = rc * kZUnitRows;
         const int jo = p.col_id[j0 + lane];
-        // stage E[., 32 genomes] (gather by original genome), P[4 rows, .]; clear the unit's Znj
+        // stage E[., 32 genomes] (gather by original genome) and P[4 rows, .]
         {
             int k = lane, jl = 0;
             while (k >= K) { k -= K; ++jl; }
@@ -114,7 +118,6 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
             const int r = idx & (kZUnitRows - 1), k = idx / kZUnitRows;
             P_w[r * K + k] = (i0 + r < I) ? p.P[(size_t)(i0 + r) + (size_t)I * k] : 0.0;
         }
-        for (int k = 0; k < K; ++k) znj[k * 32 + lane] = 0;
         __syncwarp();
 
         for (int r = 0; r < kZUnitRows; ++r) {
@@ -128,7 +131,10 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
             for (int k = 0; k < K; ++k) {
                 const double pe = Pr[k], ee = E_w[k * 33 + lane];
                 S = fma(pe, ee, S);
-                if (maybe_small) { c = c + pe * ee; cum[k * 32 + lane] = c; }
+                if (maybe_small && k < K - 1) {
+                    c = c + pe * ee;
+                    if ((k & 3) == 3 || k == K - 2) cum4[(k >> 2) * 32 + lane] = c;
+                }
             }
             const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
             const bool small = n > 0 && ok && n <= kNDirect;
@@ -141,18 +147,29 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
             if (__any_sync(kFull, small)) {
                 const int tmax = __reduce_max_sync(kFull, small ? n : 0);
                 unsigned touched = 0;
-                double ua = 0.0, ub = 0.0;
+                U4 w4 = U4{0, 0, 0, 0};
                 for (int t = 0; t < tmax; ++t) {
-                    if ((t & 1) == 0) us.pair((uint32_t)t >> 1, ua, ub);      // converged: once per two draws
+                    if ((t & 3) == 0) w4 = us.words((uint32_t)t >> 2);        // converged: once per four draws
                     if (small && t < n) {
-                        const double x = ((t & 1) ? ub : ua) * S;
-                        int pos = 0;                                          // number of thresholds <= x
+                        const uint32_t wt = (t & 2) ? ((t & 1) ? w4.w : w4.z) : ((t & 1) ? w4.y : w4.x);
+                        const double x = u32(wt) * S;
+                        int g = 0;                                            // number of group ends <= x
                         for (int step = pow2; step; step >>= 1) {
-                            const int np = pos + step;
-                            if (np <= K - 1 && cum[(np - 1) * 32 + lane] <= x) pos = np;
+                            const int np = g + step;
+                            if (np <= ng && cum4[(np - 1) * 32 + lane] <= x) g = np;
                         }
-                        zc[pos * 32 + lane] += 1;
-                        touched |= 1u << (pos & 31);
+                        int cls = K - 1;
+                        if (g < ng) {                                         // x < cum4[g]: finish inside the group
+                            double cc = g ? cum4[(g - 1) * 32 + lane] : 0.0;
+                            cls = 4 * g;
+                            for (;;) {
+                                cc = cc + Pr[cls] * E_w[cls * 33 + lane];
+                                if (x < cc || cls >= K - 2) break;
+                                ++cls;
+                            }
+                        }
+                        zc[cls * 32 + lane] += 1;
+                        touched |= 1u << (cls & 31);
                     }
                 }
                 unsigned todo = (K <= 32) ? __reduce_or_sync(kFull, touched) : 0xffffffffu;
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
                         if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
                         if (z) {
                             zc[k * 32 + lane] = 0;
-                            znj[k * 32 + lane] += z;
+                            atomicAdd(p.Znj + (size_t)k + (size_t)K * jo, z);
                             if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)jo + (size_t)J * k)] = (double)z;
                         }
                     }
@@ -173,17 +190,19 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
 
             // ---- conditional-binomial chain for the large counts (and the degenerate cells)
             if (__any_sync(kFull, (nrem | nlast) != 0)) {
-                double rem = S, u_even = 0.0, u_odd = 0.0;
+                double rem = S;
+                U4 w4 = U4{0, 0, 0, 0};
                 for (int k = 0; k <= K - 1; ++k) {
                     int z = 0;
                     if (k < K - 1) {
                         if (!__any_sync(kFull, nrem > 0)) { k = K - 2; continue; }   // jump to the remainder class
-                        if ((k & 1) == 0) us.pair((uint32_t)k >> 1, u_even, u_odd); // converged: once per two classes
+                        if ((k & 3) == 0) w4 = us.words((uint32_t)k >> 2);          // converged: once per four classes
                         if (nrem > 0) {
                             const double prob = Pr[k] * E_w[k * 33 + lane];
                             if (prob != 0.0) {
                                 const double pp = prob / rem;
-                                z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, k, (k & 1) ? u_odd : u_even, nrem, pp) : nrem;
+                                const uint32_t wk = (k & 2) ? ((k & 1) ? w4.w : w4.z) : ((k & 1) ? w4.y : w4.x);
+                                z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, k, u32(wk), nrem, pp) : nrem;
                                 nrem -= z;
                             }
                             rem = rem - prob;
@@ -195,18 +214,13 @@ __global__ void __launch_bounds__(32 * kZWarps, 8) z_alloc_fused(const ZParams p
                     if (zs) {
                         if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
                         if (z) {
-                            znj[k * 32 + lane] += z;
+                            atomicAdd(p.Znj + (size_t)k + (size_t)K * jo, z);
                             if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)jo + (size_t)J * k)] = (double)z;
                         }
                     }
                 }
             }
         }
-        if (jo >= 0)
-            for (int k = 0; k < K; ++k) {
-                const int s = znj[k * 32 + lane];
-                if (s) atomicAdd(p.Znj + (size_t)k + (size_t)K * jo, s);
-            }
         __syncwarp();
     }
 }
@@ -504,9 +518,9 @@ __global__ void test_binomial(Key key, uint32_t sweep, uint32_t stream, int kste
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     UStream us; us.init(key, sweep, stream, (uint32_t)i);
-    double u0, u1;
-    us.pair((uint32_t)kstep >> 1, u0, u1);
-    out[i] = binomial_draw(us, kstep, (kstep & 1) ? u1 : u0, n[i], pp[i]);
+    const U4 w = us.words((uint32_t)kstep >> 2);
+    const uint32_t wk = (kstep & 2) ? ((kstep & 1) ? w.w : w.z) : ((kstep & 1) ? w.y : w.x);
+    out[i] = binomial_draw(us, kstep, u32(wk), n[i], pp[i]);
 }
 __global__ void test_gamma(Key key, uint32_t sweep, uint32_t stream, const double *shape, const double *rate, double *out, int count)
 {
