@@ -34,7 +34,7 @@
  *   element: step 1/8: i + I*j ; P family (2,4,6): i + I*k ; E family (3,5,7): k + K*j
  *   u53(w0,w1) = (2*((w0>>6)<<26 | (w1>>6)) + 1) * 2^-53       in (0,1)
  *   u32(w) = (w + 1/2) * 2^-32: step-1 uniforms carry 32 random bits like R's unif_rand (Mersenne-Twister)
- *   step 1, cells with count n <= 16: direct method, n categorical draws; draw t uses word (t&3) of
+ *   step 1, cells with count n <= 32: direct method, n categorical draws; draw t uses word (t&3) of
  *                block (t>>2): x = u*S, class = first k < K-1 with x < c_k, c_k = c_{k-1} + P[i,k]*E[k,j],
  *                else the last class.  Larger cells: sequential conditional binomials (rmultinom):
  *   step 1, conditional binomial of class k: the inversion uniform is word (k&3) of block (k>>2);
@@ -59,7 +59,7 @@
 #define TINY 1e-160
 #define AUX_BLOCK 0xFFFFFFFFu
 #define BTRS_BLOCK0 0x1000u
-#define NDIRECT 16
+#define NDIRECT 32
 
 enum { ST_PERM = 0, ST_Z = 1, ST_P = 2, ST_E = 3, ST_BP = 4, ST_BE = 5, ST_AP = 6, ST_AE = 7, ST_ZINIT = 8 };
 

@@ -29,121 +29,136 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 // ------------------------------------------------------------------------------------------------
 // K1  z_alloc_fused : replaces gibbs_step1 (src/gibbs_2.cpp:85-103) + cube_sum_j/_i (:9-28)
 //
-// One thread per (context, genome) cell; a warp owns a unit of 32 genomes x 4 context rows and
-// works alone (private shared memory, no block barrier; units are claimed heaviest-first from a
-// global counter).  Per row the 32 lanes draw their cells' allocations with the per-count switch
-// of the draw specification:
-//   n <= 16 : direct method -- n categorical draws by binary search in the lane's cumulative
-//             P[i,.] o E[.,j]; the Philox block of four draws is generated warp-converged;
-//   n  > 16 : R's rmultinom structure -- the K classes in lockstep, one conditional binomial each.
-// The class counts are reduced on the spot: over the 32 genomes with one REDUX (-> Zin, one
-// integer atomic per row/class/warp); the per-genome sums Znj take one integer atomic per non-zero
-// count (fire-and-forget reductions into L2).  Z itself is never written (except, on request, the final
-// sweep's cube for the reference's `Zs`).
-//
-// Genomes are visited in a kernel-private order, sorted by mutation burden (col_id maps a
-// position to the original genome): neighbouring lanes then hold similar counts, so they take the
-// same sampler branch with similar trip counts.  Random streams, Znj and the cube are addressed
-// by the ORIGINAL genome index, so the order cannot change any result.
+// The counts M never change during a chain, so the non-zero cells are listed ONCE, sorted by count
+// (largest first; ties in genome-major order), and every launch walks that list: a warp takes 32
+// consecutive cells -- cells of (nearly) the same count, so the lanes run the same sampler with
+// the same trip count -- one thread per cell:
+//   * the lane stages its cell's K products P[i,k]*E[k,j] in shared memory (prob[k][lane]) while
+//     summing S = sum_k P E (fma chain) and, for small counts, the cumulative sums;
+//   * n <= 32 : direct method -- n categorical draws by binary search in the cumulative sums; the
+//     Philox block of four draws is generated warp-converged;
+//   * n  > 32 : R's rmultinom structure -- the K classes in lockstep, one conditional binomial
+//     each (inversion below n*p < 30, BTRS above), early exit when every lane is done.
+// The class counts are reduced on the spot and Z is never written (except, on request, the final
+// sweep's cube for the reference's `Zs`): sum_j Z goes to a block-wide shared-memory Zin (integer
+// atomics, flushed once per block) and sum_i Z straight to L2 integer atomics, one per non-zero
+// count.  Work is claimed heaviest-first from a global counter, two batches at a time.
 // ------------------------------------------------------------------------------------------------
-constexpr int kZUnitRows = 4;     // context rows per unit
-constexpr int kZWarps = 2;        // independent warps per block
-constexpr int kNDirect = 16;      // largest count drawn by the direct method
+constexpr int kZWarps = 8;        // warps per block (they share only the block's Zin accumulator)
+constexpr int kZChunk = 2;        // batches of 32 cells claimed at a time
+constexpr int kNDirect = 32;      // largest count drawn by the direct method
+constexpr int kZinSmemMax = 40 * 1024;
 
 struct ZParams {
-    int I, J, Jp, K;
-    const int *M;               // [I][Jp], columns in burden order
-    const int *col_id;          // [Jp] original genome of each position, -1 for padding
+    int I, J, K;
+    const unsigned short *cell_row;   // [n_cells] context of each listed cell
+    const int *cell_col;              // [n_cells] genome
+    const int *cell_n;                // [n_cells] count, non-increasing
+    int n_cells, n_batches;
     const double *P, *E;
     int *Zin, *Znj;             // accumulated with integer atomics; zeroed by the previous launch
     int *Zin_next, *Znj_next;   // the other half of the ping-pong, zeroed by this launch
     double *Zcube;              // optional I x J x K (pre-zeroed) for the last Z (src/gibbs_2.cpp:323)
-    unsigned long long *unit_counter;
-    unsigned long long unit_base;
-    int n_rc, n_units;          // row chunks per column tile, units in total
+    unsigned long long *counter;
+    unsigned long long base;
     int warp_smem;              // bytes of shared memory per warp
+    int zin_smem;               // 1: accumulate Zin in shared memory per block
     Key key;
     uint32_t sweep, stream;
 };
 
-// per warp: E_w [K][33] f64, cum4 [ceil((K-1)/4)][32] f64, P_w [4][K] f64, zc [K][32] u8
+// per warp: prob [K][32] f64, cum4 [ceil((K-1)/4)][32] f64, zc [K][32] u8 ; per block: Zin [I*K] i32
 inline int z_groups(int K) { return (K - 1 + 3) / 4; }
 inline size_t z_smem_bytes_per_warp(int K)
 {
-    return (size_t)8 * ((size_t)K * 33 + (size_t)z_groups(K) * 32 + (size_t)kZUnitRows * K) + ((size_t)K * 32 + 7) / 8 * 8;
+    return (size_t)8 * ((size_t)K * 32 + (size_t)z_groups(K) * 32) + ((size_t)K * 32 + 7) / 8 * 8;
 }
 
-__global__ void __launch_bounds__(32 * kZWarps, 12) z_alloc_fused(const ZParams p)
+SG_D void z_emit(const ZParams &p, int *zin_s, int row, int col, int k, int z)
+{
+    if (zin_s) atomicAdd(zin_s + row + p.I * k, z);
+    else atomicAdd(p.Zin + (size_t)row + (size_t)p.I * k, z);
+    atomicAdd(p.Znj + (size_t)k + (size_t)p.K * col, z);
+    if (p.Zcube) p.Zcube[(size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k)] = (double)z;
+}
+
+__global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int I = p.I, J = p.J, K = p.K;
     unsigned char *base = smem_raw + (size_t)warp * p.warp_smem;
-    double *E_w = reinterpret_cast<double *>(base);
     const int ng = (K - 1 + 3) / 4;                         // groups of four thresholds
-    double *cum4 = E_w + K * 33;                            // cumulative P o E at the end of each group
-    double *P_w = cum4 + ng * 32;
-    unsigned char *zc = reinterpret_cast<unsigned char *>(P_w + kZUnitRows * K);
+    double *prob = reinterpret_cast<double *>(base);        // [K][32] this lane's P[i,k]*E[k,j]
+    double *cum4 = prob + K * 32;                           // cumulative sums at the end of each group
+    unsigned char *zc = reinterpret_cast<unsigned char *>(cum4 + ng * 32);
+    int *zin_s = p.zin_smem ? reinterpret_cast<int *>(smem_raw + (size_t)kZWarps * p.warp_smem) : nullptr;
 
     // zero the other half of the ping-pong for the next launch
     {
-        const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+        const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gsz = (size_t)gridDim.x * blockDim.x;
         for (size_t i = gtid; i < (size_t)I * K; i += gsz) p.Zin_next[i] = 0;
         for (size_t i = gtid; i < (size_t)K * J; i += gsz) p.Znj_next[i] = 0;
+    }
+    if (zin_s) {
+        for (int i = tid; i < I * K; i += 32 * kZWarps) zin_s[i] = 0;
+        __syncthreads();
     }
     for (int k = 0; k < K; ++k) zc[k * 32 + lane] = 0;      // invariant: all zero between cells
     int pow2 = 0;                                           // largest power of two <= ng
     if (ng > 0) { pow2 = 1; while (pow2 * 2 <= ng) pow2 *= 2; }
+    const bool vec2 = (K & 1) == 0;
 
     for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = (int)(atomicAdd(p.unit_counter, 1ULL) - p.unit_base);
-        unit = __shfl_sync(kFull, unit, 0);
-        if (unit >= p.n_units) break;
-        const int ct = unit / p.n_rc, rc = unit - ct * p.n_rc;
-        const int j0 = ct * 32, i0 = rc * kZUnitRows;
-        const int jo = p.col_id[j0 + lane];
-        // stage E[., 32 genomes] (gather by original genome) and P[4 rows, .]
-        {
-            int k = lane, jl = 0;
-            while (k >= K) { k -= K; ++jl; }
-            for (int idx = lane; idx < K * 32; idx += 32) {
-                const int js = __shfl_sync(kFull, jo, jl);
-                E_w[k * 33 + jl] = (js >= 0) ? p.E[(size_t)K * js + k] : 0.0;
-                k += 32;
-                while (k >= K) { k -= K; ++jl; }
-            }
-        }
-        for (int idx = lane; idx < kZUnitRows * K; idx += 32) {
-            const int r = idx & (kZUnitRows - 1), k = idx / kZUnitRows;
-            P_w[r * K + k] = (i0 + r < I) ? p.P[(size_t)(i0 + r) + (size_t)I * k] : 0.0;
-        }
-        __syncwarp();
+        long long chunk = 0;
+        if (lane == 0) chunk = (long long)(atomicAdd(p.counter, 1ULL) - p.base);
+        chunk = __shfl_sync(kFull, chunk, 0);
+        if (chunk * kZChunk >= p.n_batches) break;
+        for (int bb = 0; bb < kZChunk; ++bb) {
+            const int batch = (int)chunk * kZChunk + bb;
+            if (batch >= p.n_batches) break;
+            const int cell = batch * 32 + lane;
+            const bool valid = cell < p.n_cells;
+            const int n = valid ? p.cell_n[cell] : 0;
+            const int row = valid ? (int)p.cell_row[cell] : 0;
+            const int col = valid ? p.cell_col[cell] : 0;
+            const bool maybe_small = __any_sync(kFull, valid && n <= kNDirect);
 
-        for (int r = 0; r < kZUnitRows; ++r) {
-            const int row = i0 + r;
-            if (row >= I) break;
-            const int n = (jo >= 0) ? p.M[(size_t)row * p.Jp + j0 + lane] : 0;
-            if (!__any_sync(kFull, n > 0)) continue;
-            const double *Pr = P_w + r * K;
-            const bool maybe_small = __any_sync(kFull, n > 0 && n <= kNDirect);
+            // stage P[i,.] o E[.,j]; S = fma chain; cumulative sums for the direct method
+            const double *Pr = p.P + row;
+            const double *Ec = p.E + (size_t)K * col;
             double S = 0.0, c = 0.0;
-            for (int k = 0; k < K; ++k) {
-                const double pe = Pr[k], ee = E_w[k * 33 + lane];
-                S = fma(pe, ee, S);
-                if (maybe_small && k < K - 1) {
-                    c = c + pe * ee;
-                    if ((k & 3) == 3 || k == K - 2) cum4[(k >> 2) * 32 + lane] = c;
+            if (vec2) {
+                for (int k = 0; k < K; k += 2) {
+                    const double2 ee = *reinterpret_cast<const double2 *>(Ec + k);
+                    const double p0 = __ldg(Pr + (size_t)I * k), p1 = __ldg(Pr + (size_t)I * (k + 1));
+                    S = fma(p0, ee.x, S);
+                    S = fma(p1, ee.y, S);
+                    const double q0 = p0 * ee.x, q1 = p1 * ee.y;
+                    prob[k * 32 + lane] = q0;
+                    prob[(k + 1) * 32 + lane] = q1;
+                    if (maybe_small) {
+                        if (k < K - 1) { c = c + q0; if ((k & 3) == 3 || k == K - 2) cum4[(k >> 2) * 32 + lane] = c; }
+                        if (k + 1 < K - 1) { c = c + q1; if (((k + 1) & 3) == 3 || k + 1 == K - 2) cum4[((k + 1) >> 2) * 32 + lane] = c; }
+                    }
+                }
+            } else {
+                for (int k = 0; k < K; ++k) {
+                    const double ee = Ec[k], pe = __ldg(Pr + (size_t)I * k);
+                    S = fma(pe, ee, S);
+                    const double q0 = pe * ee;
+                    prob[k * 32 + lane] = q0;
+                    if (maybe_small && k < K - 1) { c = c + q0; if ((k & 3) == 3 || k == K - 2) cum4[(k >> 2) * 32 + lane] = c; }
                 }
             }
             const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
-            const bool small = n > 0 && ok && n <= kNDirect;
-            int nrem = (n > kNDirect && ok) ? n : 0;
-            const int nlast = (n > 0 && !ok) ? n : 0;       // degenerate probabilities: all to the last class
+            const bool small = valid && ok && n <= kNDirect;
+            int nrem = (valid && ok && n > kNDirect) ? n : 0;
+            const int nlast = (valid && !ok) ? n : 0;       // degenerate probabilities: all to the last class
             UStream us;
-            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * jo));
+            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * col));
 
-            // ---- direct method for the small counts of this row
+            // ---- direct method
             if (__any_sync(kFull, small)) {
                 const int tmax = __reduce_max_sync(kFull, small ? n : 0);
                 unsigned touched = 0;
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 12) z_alloc_fused(const ZParams 
                             double cc = g ? cum4[(g - 1) * 32 + lane] : 0.0;
                             cls = 4 * g;
                             for (;;) {
-                                cc = cc + Pr[cls] * E_w[cls * 33 + lane];
+                                cc = cc + prob[cls * 32 + lane];
                                 if (x < cc || cls >= K - 2) break;
                                 ++cls;
                             }
@@ -172,18 +187,13 @@ __global__ void __launch_bounds__(32 * kZWarps, 12) z_alloc_fused(const ZParams 
                         touched |= 1u << (cls & 31);
                     }
                 }
-                unsigned todo = (K <= 32) ? __reduce_or_sync(kFull, touched) : 0xffffffffu;
+                const unsigned todo = (K <= 32) ? __reduce_or_sync(kFull, touched) : 0xffffffffu;
                 for (int k = 0; k < K; ++k) {
                     if (K <= 32 && !((todo >> k) & 1u)) continue;
                     const int z = zc[k * 32 + lane];
-                    const int zs = __reduce_add_sync(kFull, z);
-                    if (zs) {
-                        if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
-                        if (z) {
-                            zc[k * 32 + lane] = 0;
-                            atomicAdd(p.Znj + (size_t)k + (size_t)K * jo, z);
-                            if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)jo + (size_t)J * k)] = (double)z;
-                        }
+                    if (z) {
+                        zc[k * 32 + lane] = 0;
+                        z_emit(p, zin_s, row, col, k, z);
                     }
                 }
             }
@@ -198,30 +208,30 @@ __global__ void __launch_bounds__(32 * kZWarps, 12) z_alloc_fused(const ZParams 
                         if (!__any_sync(kFull, nrem > 0)) { k = K - 2; continue; }   // jump to the remainder class
                         if ((k & 3) == 0) w4 = us.words((uint32_t)k >> 2);          // converged: once per four classes
                         if (nrem > 0) {
-                            const double prob = Pr[k] * E_w[k * 33 + lane];
-                            if (prob != 0.0) {
-                                const double pp = prob / rem;
+                            const double pk = prob[k * 32 + lane];
+                            if (pk != 0.0) {
+                                const double pp = pk / rem;
                                 const uint32_t wk = (k & 2) ? ((k & 1) ? w4.w : w4.z) : ((k & 1) ? w4.y : w4.x);
                                 z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, k, u32(wk), nrem, pp) : nrem;
                                 nrem -= z;
                             }
-                            rem = rem - prob;
+                            rem = rem - pk;
                         }
                     } else {
                         z = nrem + nlast;
                     }
-                    const int zs = __reduce_add_sync(kFull, z);
-                    if (zs) {
-                        if (lane == 0) atomicAdd(p.Zin + (size_t)row + (size_t)I * k, zs);
-                        if (z) {
-                            atomicAdd(p.Znj + (size_t)k + (size_t)K * jo, z);
-                            if (p.Zcube) p.Zcube[(size_t)row + (size_t)I * ((size_t)jo + (size_t)J * k)] = (double)z;
-                        }
-                    }
+                    if (z) z_emit(p, zin_s, row, col, k, z);
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
+    }
+    if (zin_s) {
+        __syncthreads();
+        for (int i = tid; i < I * K; i += 32 * kZWarps) {
+            const int v = zin_s[i];
+            if (v) atomicAdd(p.Zin + i, v);
+        }
     }
 }
 
@@ -316,7 +326,8 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
 // ------------------------------------------------------------------------------------------------
 // KE  e_family : gibbs_step3/5/7 (src/gibbs_2.cpp:123-137,156-169,213-251) on K x J,
 //     corrP = P' W (:128) in front, corrE = W E' (:111) segment partials behind.
-// grid = (segments of 128 columns, k-splits); thread = (column, k-group lane)
+// grid = (segments of 128 genomes, groups of 4 classes); thread = (genome, pair of classes).
+// Latency-bound element-wise work: everything is resident in one wave, two elements per thread.
 // ------------------------------------------------------------------------------------------------
 struct EParams {
     int I, J, Jp, K;
@@ -325,7 +336,6 @@ struct EParams {
     double *E, *Ae, *Be;
     const int *Znj;
     double *corrE_part;         // [n_seg][I*K]
-    int kg_per_split;           // k-groups (of 4) per blockIdx.y
     int do_corrE;
     double *Es_slot, *Aes_slot, *Bes_slot;
     Hyper h;
@@ -334,64 +344,62 @@ struct EParams {
     Ops ops;
 };
 
-inline size_t e_smem_bytes(int kg_per_split) { return sizeof(double) * (size_t)kSeg * (size_t)(4 * kg_per_split); }
+constexpr int kEGroup = 4;      // classes per block
+
+SG_D void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
+{
+    double E = p.E[e], Ae = p.Ae[e], Be = p.Be[e];
+    for (int o = 0; o < p.ops.n; ++o) {
+        const int op = p.ops.get(o);
+        if (op == 3) {
+            UStream us; us.init(p.key, p.sweep, kStE, (uint32_t)e);
+            const double shape = Ae + 1 + (double)p.Znj[e];
+            const double rate = Be + corrP;
+            E = gamma_draw(us, shape, rate);
+        } else if (op == 5) {
+            Be = update_b(p.key, p.sweep, kStBe, (uint32_t)e, Ae, E, p.h.ae, p.h.be);
+        } else if (op == 7) {
+            Ae = update_a(p.key, p.sweep, kStAe, (uint32_t)e, Ae, E, Be, p.h.le, p.h.var_ae);
+        }
+    }
+    p.E[e] = E; p.Ae[e] = Ae; p.Be[e] = Be;
+    if (p.Es_slot) p.Es_slot[e] = E;
+    if (p.Aes_slot) p.Aes_slot[e] = Ae;
+    if (p.Bes_slot) p.Bes_slot[e] = Be;
+    Eo = E;
+}
 
 __global__ void __launch_bounds__(kEThreads) e_family(const EParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *E_s = reinterpret_cast<double *>(smem_raw);   // [128][Kloc]
-    const int tid = threadIdx.x, jl = tid & (kSeg - 1), q = tid >> 7;
+    __shared__ double E_s[kSeg * kEGroup];                // [128][4]
+    const int tid = threadIdx.x, jl = tid & (kSeg - 1), h = tid >> 7;
     const int I = p.I, J = p.J, K = p.K;
     const int seg = blockIdx.x, j0 = seg * kSeg, j = j0 + jl;
-    const int kBegin = blockIdx.y * p.kg_per_split * 4;
-    const int kEnd = min(K, kBegin + p.kg_per_split * 4);
-    const int Kloc = p.kg_per_split * 4;
+    const int kBegin = blockIdx.y * kEGroup;
+    const int kEnd = min(K, kBegin + kEGroup);
+    const int ka = kBegin + 2 * h, kb = ka + 1;           // this thread's two classes
     bool has3 = false;
     for (int o = 0; o < p.ops.n; ++o) has3 |= (p.ops.get(o) == 3);
 
-    if (j < J) {
-        for (int k0 = kBegin + 4 * q; k0 < kEnd; k0 += 8) {
-            const int nk = min(4, kEnd - k0);
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            if (has3) {
-                const double *Wc = p.W + j;
-                const double *P0 = p.P + (size_t)I * k0;
-                const double *P1 = p.P + (size_t)I * min(k0 + 1, K - 1);
-                const double *P2 = p.P + (size_t)I * min(k0 + 2, K - 1);
-                const double *P3 = p.P + (size_t)I * min(k0 + 3, K - 1);
-#pragma unroll 4
-                for (int i = 0; i < I; ++i) {
-                    const double w = Wc[(size_t)i * p.Jp];
-                    acc0 = fma(__ldg(P0 + i), w, acc0);
-                    acc1 = fma(__ldg(P1 + i), w, acc1);
-                    acc2 = fma(__ldg(P2 + i), w, acc2);
-                    acc3 = fma(__ldg(P3 + i), w, acc3);
-                }
+    if (j < J && ka < kEnd) {
+        double acc0 = 0.0, acc1 = 0.0;
+        if (has3) {
+            const double *Wc = p.W + j;
+            const double *P0 = p.P + (size_t)I * ka;
+            const double *P1 = p.P + (size_t)I * min(kb, K - 1);
+#pragma unroll 8
+            for (int i = 0; i < I; ++i) {
+                const double w = Wc[(size_t)i * p.Jp];
+                acc0 = fma(__ldg(P0 + i), w, acc0);
+                acc1 = fma(__ldg(P1 + i), w, acc1);
             }
-            for (int c = 0; c < nk; ++c) {
-                const int k = k0 + c;
-                const size_t e = (size_t)k + (size_t)K * j;
-                double E = p.E[e], Ae = p.Ae[e], Be = p.Be[e];
-                const double corrP = (c == 0) ? acc0 : (c == 1) ? acc1 : (c == 2) ? acc2 : acc3;
-                for (int o = 0; o < p.ops.n; ++o) {
-                    const int op = p.ops.get(o);
-                    if (op == 3) {
-                        UStream us; us.init(p.key, p.sweep, kStE, (uint32_t)e);
-                        const double shape = Ae + 1 + (double)p.Znj[e];
-                        const double rate = Be + corrP;
-                        E = gamma_draw(us, shape, rate);
-                    } else if (op == 5) {
-                        Be = update_b(p.key, p.sweep, kStBe, (uint32_t)e, Ae, E, p.h.ae, p.h.be);
-                    } else if (op == 7) {
-                        Ae = update_a(p.key, p.sweep, kStAe, (uint32_t)e, Ae, E, Be, p.h.le, p.h.var_ae);
-                    }
-                }
-                p.E[e] = E; p.Ae[e] = Ae; p.Be[e] = Be;
-                if (p.Es_slot) p.Es_slot[e] = E;
-                if (p.Aes_slot) p.Aes_slot[e] = Ae;
-                if (p.Bes_slot) p.Bes_slot[e] = Be;
-                E_s[jl * Kloc + (k - kBegin)] = E;
-            }
+        }
+        double Eo;
+        e_update_element(p, (size_t)ka + (size_t)K * j, acc0, Eo);
+        E_s[jl * kEGroup + (ka - kBegin)] = Eo;
+        if (kb < kEnd) {
+            e_update_element(p, (size_t)kb + (size_t)K * j, acc1, Eo);
+            E_s[jl * kEGroup + (kb - kBegin)] = Eo;
         }
     }
     if (!p.do_corrE) return;
@@ -400,10 +408,20 @@ __global__ void __launch_bounds__(kEThreads) e_family(const EParams p)
     const int Kn = kEnd - kBegin;
     for (int o = tid; o < I * Kn; o += kEThreads) {
         const int i = o / Kn, kk = o - i * Kn;
-        const double *Wr = p.W + (size_t)i * p.Jp + j0;
+        const double *Wr = p.W + (size_t)i * p.Jp + j0;    // 16-byte aligned: Jp and j0 are multiples of 32
         double acc = 0.0;
-#pragma unroll 4
-        for (int c = 0; c < jn; ++c) acc = fma(Wr[c], E_s[c * Kloc + kk], acc);
+        int c = 0;
+        for (; c + 16 <= jn; c += 16) {
+            double2 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const double2 *>(Wr + c + 2 * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc = fma(w[u].x, E_s[(c + 2 * u) * kEGroup + kk], acc);
+                acc = fma(w[u].y, E_s[(c + 2 * u + 1) * kEGroup + kk], acc);
+            }
+        }
+        for (; c < jn; ++c) acc = fma(Wr[c], E_s[c * kEGroup + kk], acc);
         p.corrE_part[(size_t)seg * ((size_t)I * K) + (size_t)i + (size_t)I * (kBegin + kk)] = acc;
     }
 }

@@ -48,15 +48,17 @@ constexpr size_t kRingBytes = size_t(3) << 30;   // per ring set (two sets)
 // The data of one cohort on one device, shared by every chain on that device.
 struct DeviceData {
     int device = 0, I = 0, J = 0, Jp = 0, n2 = 0;
-    int *M = nullptr;          // [I][Jp], columns in z_alloc's burden order
-    int *col_id = nullptr;     // [Jp] original genome of each position of M (-1: padding)
+    // z_alloc's work list: the non-zero cells sorted by count (largest first, ties genome-major)
+    unsigned short *cell_row = nullptr;
+    int *cell_col = nullptr, *cell_n = nullptr;
+    int n_cells = 0;
     int *Mrow = nullptr;       // [I][Jp], original genome order (log-likelihood)
     double *W = nullptr;       // [I][Jp]
     double *lgm = nullptr;     // sum lgamma(M+1), one double
     ~DeviceData()
     {
         cudaSetDevice(device);
-        cudaFree(M); cudaFree(Mrow); cudaFree(col_id); cudaFree(W); cudaFree(lgm);
+        cudaFree(cell_row); cudaFree(cell_col); cudaFree(cell_n); cudaFree(Mrow); cudaFree(W); cudaFree(lgm);
     }
 };
 
@@ -68,35 +70,43 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
     auto d = std::make_shared<DeviceData>();
     d->device = device; d->I = I; d->J = J; d->Jp = (J + 31) / 32 * 32;
     d->n2 = 1; while (d->n2 < J) d->n2 <<= 1;
+    if (I > 65535) return fail(SIGNER_ERR_ARG, "problem: I must be below 65536");
     const size_t n = (size_t)I * d->Jp;
-    std::vector<int> m(n, 0), msort(n, 0);
+    std::vector<int> m(n, 0);
     std::vector<double> w(n, 0.0);
-    std::vector<long long> burden(J, 0);
+    std::vector<int> cells;                  // element ids i + I*j of the non-zero cells, genome-major
     for (int j = 0; j < J; ++j)
         for (int i = 0; i < I; ++i) {
             const double mv = M[(size_t)i + (size_t)I * j], wv = W[(size_t)i + (size_t)I * j];
             if (!(mv >= 0.0) || !(mv <= 2147483647.0)) return fail(SIGNER_ERR_NONFINITE, "M has a negative, non-finite or too large entry");
             if (!(wv >= 0.0) || !(wv <= 1.7976931348623157e308)) return fail(SIGNER_ERR_NONFINITE, "W has a negative or non-finite entry");
-            m[(size_t)i * d->Jp + j] = (int)mv;          // int size (src/gibbs_2.cpp:31)
+            const int mi = (int)mv;                      // int size (src/gibbs_2.cpp:31)
+            m[(size_t)i * d->Jp + j] = mi;
             w[(size_t)i * d->Jp + j] = wv;
-            burden[j] += (long long)(int)mv;
+            if (mi > 0) cells.push_back(i + I * j);
         }
-    // z_alloc_fused visits the genomes in order of decreasing burden (a private order: results do not depend on it)
-    std::vector<int> order(J), col_id(d->Jp, -1);
-    for (int j = 0; j < J; ++j) order[j] = j;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return burden[a] > burden[b]; });
-    for (int pos = 0; pos < J; ++pos) {
-        col_id[pos] = order[pos];
-        for (int i = 0; i < I; ++i) msort[(size_t)i * d->Jp + pos] = m[(size_t)i * d->Jp + order[pos]];
+    // z_alloc_fused's work list (a private order: results do not depend on it)
+    std::stable_sort(cells.begin(), cells.end(), [&](int a, int b) {
+        return m[(size_t)(a % I) * d->Jp + a / I] > m[(size_t)(b % I) * d->Jp + b / I];
+    });
+    d->n_cells = (int)cells.size();
+    const size_t nc = std::max<size_t>(cells.size(), 1);
+    std::vector<unsigned short> crow(nc, 0);
+    std::vector<int> ccol(nc, 0), cn(nc, 0);
+    for (size_t t = 0; t < cells.size(); ++t) {
+        const int i = cells[t] % I, j = cells[t] / I;
+        crow[t] = (unsigned short)i; ccol[t] = j; cn[t] = m[(size_t)i * d->Jp + j];
     }
-    CU(cudaMalloc(&d->M, n * sizeof(int)));
+    CU(cudaMalloc(&d->cell_row, nc * sizeof(unsigned short)));
+    CU(cudaMalloc(&d->cell_col, nc * sizeof(int)));
+    CU(cudaMalloc(&d->cell_n, nc * sizeof(int)));
     CU(cudaMalloc(&d->Mrow, n * sizeof(int)));
-    CU(cudaMalloc(&d->col_id, (size_t)d->Jp * sizeof(int)));
     CU(cudaMalloc(&d->W, n * sizeof(double)));
     CU(cudaMalloc(&d->lgm, sizeof(double)));
-    CU(cudaMemcpy(d->M, msort.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->cell_row, crow.data(), nc * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->cell_col, ccol.data(), nc * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d->cell_n, cn.data(), nc * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d->Mrow, m.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d->col_id, col_id.data(), (size_t)d->Jp * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d->W, w.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     // constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180)
     double *col = nullptr;
@@ -136,8 +146,8 @@ struct signer_chain {
     double *stats = nullptr;
     unsigned long long *tile_counter = nullptr;
     unsigned long long z_launches = 0;
-    int z_grid = 0, n_rc = 0, n_units = 0, z_warp_smem = 0;
-    int kg_per_split = 2, ksplit = 1;
+    int z_grid = 0, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
+    int ksplit = 1;
     Hyper h{};
     Key key{};
     uint32_t sweep0 = 0;
@@ -209,19 +219,21 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
 {
     const int tgt = c->zcur ^ 1;
     ZParams p{};
-    p.I = c->I; p.J = c->J; p.Jp = c->Jp; p.K = c->K;
-    p.M = c->data->M; p.col_id = c->data->col_id; p.P = c->P; p.E = c->E;
+    p.I = c->I; p.J = c->J; p.K = c->K;
+    p.cell_row = c->data->cell_row; p.cell_col = c->data->cell_col; p.cell_n = c->data->cell_n;
+    p.n_cells = c->data->n_cells; p.n_batches = c->n_batches;
+    p.P = c->P; p.E = c->E;
     p.Zin = c->Zin[tgt]; p.Znj = c->Znj[tgt];
     p.Zin_next = c->Zin[c->zcur]; p.Znj_next = c->Znj[c->zcur];
     p.Zcube = zcube;
-    p.unit_counter = c->tile_counter;
-    p.unit_base = c->z_launches * (unsigned long long)(c->n_units + c->z_grid * kZWarps);   // every warp overshoots once
-    p.n_rc = c->n_rc; p.n_units = c->n_units; p.warp_smem = c->z_warp_smem;
+    p.counter = c->tile_counter;
+    p.base = c->z_launches * (unsigned long long)(c->n_chunks + c->z_grid * kZWarps);   // every warp overshoots once
+    p.warp_smem = c->z_warp_smem; p.zin_smem = c->z_zin_smem;
     p.key = c->key; p.sweep = sweep; p.stream = stream_id;
     if (zcube) CU(cudaMemsetAsync(zcube, 0, sizeof(double) * (size_t)c->I * c->J * c->K, c->stream));
     {
         ProfScope ps(c, 0);
-        z_alloc_fused<<<c->z_grid, 32 * kZWarps, (size_t)c->z_warp_smem * kZWarps, c->stream>>>(p);
+        z_alloc_fused<<<c->z_grid, 32 * kZWarps, (size_t)c->z_warp_smem * kZWarps + (c->z_zin_smem ? c->nP * sizeof(int) : 0), c->stream>>>(p);
     }
     CU(cudaGetLastError());
     c->z_launches++;
@@ -252,12 +264,12 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     p.I = c->I; p.J = c->J; p.Jp = c->Jp; p.K = c->K;
     p.W = c->data->W; p.P = c->P; p.E = c->E; p.Ae = c->Ae; p.Be = c->Be;
     p.Znj = c->Znj[c->zcur]; p.corrE_part = c->corrE_part;
-    p.kg_per_split = c->kg_per_split; p.do_corrE = do_corrE;
+    p.do_corrE = do_corrE;
     p.Es_slot = Es; p.Aes_slot = Aes; p.Bes_slot = Bes;
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
     {
         ProfScope ps(c, 2);
-        e_family<<<dim3(c->n_seg, c->ksplit), kEThreads, e_smem_bytes(c->kg_per_split), c->stream>>>(p);
+        e_family<<<dim3(c->n_seg, c->ksplit), kEThreads, 0, c->stream>>>(p);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -427,19 +439,18 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     CU(cudaMalloc(&c->stats, 8 * sizeof(double)));
 
     // launch geometry
-    c->n_rc = (c->I + kZUnitRows - 1) / kZUnitRows;
-    c->n_units = c->n_rc * (c->Jp / 32);
+    c->n_batches = (data->n_cells + 31) / 32;
+    c->n_chunks = (c->n_batches + kZChunk - 1) / kZChunk;
     c->z_warp_smem = (int)z_smem_bytes_per_warp(K);
-    const size_t zsm = (size_t)c->z_warp_smem * kZWarps;
+    c->z_zin_smem = (c->nP * sizeof(int) <= (size_t)kZinSmemMax) ? 1 : 0;
+    const size_t zsm = (size_t)c->z_warp_smem * kZWarps + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
     int occ = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * kZWarps, zsm));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     if (occ < 1) return fail(SIGNER_ERR_ARG, "z_alloc_fused does not fit on an SM for this K");
-    c->z_grid = std::max(1, std::min((c->n_units + kZWarps - 1) / kZWarps, occ * sms));
-    const int nkg = (K + 3) / 4;
-    c->kg_per_split = 2;
-    c->ksplit = (nkg + c->kg_per_split - 1) / c->kg_per_split;
+    c->z_grid = std::max(1, std::min((c->n_chunks + kZWarps - 1) / kZWarps, occ * sms));
+    c->ksplit = (K + kEGroup - 1) / kEGroup;
 
     // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device
     if (st->Z) {
