@@ -36,9 +36,10 @@
  *   u32(w) = (w + 1/2) * 2^-32: step-1 uniforms carry 32 random bits like R's unif_rand (Mersenne-Twister)
  *   step 1, cells with count n <= 32: direct method, n categorical draws; draw t uses word (t&3) of
  *                block (t>>2): x = u*S, class = first k < K-1 with x < c_k, c_k = c_{k-1} + P[i,k]*E[k,j],
- *                else the last class.  Larger cells: sequential conditional binomials (rmultinom):
- *   step 1, conditional binomial of class k: the inversion uniform is word (k&3) of block (k>>2);
- *                BTRS attempt t of class k reads block 0x1000 + (k<<8) + t (U from word 0, V from word 1)
+ *                else the last class.  Larger cells: sequential conditional binomials (rmultinom), the
+ *                classes visited heaviest first (running argmax of P*E, ties to the lowest index):
+ *   step 1, conditional binomial number t: the inversion uniform is word (t&3) of block (t>>2);
+ *                BTRS attempt a of binomial t reads block 0x1000 + (t<<8) + a (U from word 0, V from word 1)
  *   gamma draws: Marsaglia-Tsang attempt t uses block t: x = ppnd16(u(w0,w1)), accept test u(w2,w3);
  *                block 0xFFFFFFFF gives (boost uniform for shape<1, MH acceptance uniform)
  *   binomial(n,pp): p=min(pp,1-pp); n*p<30 -> inversion from q^n (binary powering), recurrence
@@ -60,6 +61,7 @@
 #define AUX_BLOCK 0xFFFFFFFFu
 #define BTRS_BLOCK0 0x1000u
 #define NDIRECT 32
+#define ORACLE_KMAX 128
 
 enum { ST_PERM = 0, ST_Z = 1, ST_P = 2, ST_E = 3, ST_BP = 4, ST_BE = 5, ST_AP = 6, ST_AE = 7, ST_ZINIT = 8 };
 
@@ -434,19 +436,32 @@ static void multinomial_cell(uint64_t seed, uint32_t sweep, uint32_t stream, int
         }
         return;
     }
+    /* Large counts: sequential conditional binomials as in R's rmultinom (zero-probability skip,
+     * pp<1 test, early exit at n<=0, remainder to the class visited last), but the classes are
+     * visited heaviest first: step t takes the not-yet-visited class with the largest P*E (ties:
+     * lowest index).  The multinomial law does not depend on the visiting order; the order makes
+     * the lanes of a GPU warp meet their expensive draws at the same step and lets the chain stop
+     * after the few classes that carry the mass. */
+    double prob[ORACLE_KMAX];
+    unsigned char used[ORACLE_KMAX];
+    for (int m = 0; m < K; m++) { prob[m] = P[s + (size_t)I * m] * E[m + (size_t)K * g]; used[m] = 0; }
     double rem = S;
-    for (int m = 0; m < K - 1; m++) {
-        double prob = P[s + (size_t)I * m] * E[m + (size_t)K * g];
-        if (prob != 0.0) {
-            double pp = prob / rem;
-            int zz = (pp > 0.0 && pp < 1.0) ? binomial_draw(&us, m, n, pp) : n;
-            z[m * zs] = (double)zz;
+    int cur = -1;
+    for (int t = 0; t < K; t++) {
+        double best = -1.0; cur = -1;
+        for (int m = 0; m < K; m++) if (!used[m] && prob[m] > best) { best = prob[m]; cur = m; }
+        used[cur] = 1;
+        if (t == K - 1) break;                       /* the last class takes the remainder */
+        if (best != 0.0) {
+            double pp = best / rem;
+            int zz = (pp > 0.0 && pp < 1.0) ? binomial_draw(&us, t, n, pp) : n;
+            z[cur * zs] = (double)zz;
             n -= zz;
         }
         if (n <= 0) break;
-        rem = rem - prob;
+        rem = rem - best;
     }
-    if (n > 0) z[(K - 1) * zs] = (double)n;
+    if (n > 0) z[cur * zs] += (double)n;
 }
 
 /* step 1 -- src/gibbs_2.cpp:85-103 */

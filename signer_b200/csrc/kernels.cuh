@@ -37,8 +37,9 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 //     summing S = sum_k P E (fma chain) and, for small counts, the cumulative sums;
 //   * n <= 32 : direct method -- n categorical draws by binary search in the cumulative sums; the
 //     Philox block of four draws is generated warp-converged;
-//   * n  > 32 : R's rmultinom structure -- the K classes in lockstep, one conditional binomial
-//     each (inversion below n*p < 30, BTRS above), early exit when every lane is done.
+//   * n  > 32 : R's rmultinom structure -- conditional binomials in lockstep (inversion below
+//     n*p < 30, BTRS above), each lane visiting its classes heaviest first, so the lanes meet their
+//     expensive draws together and the loop ends once the classes that carry the mass are done.
 // The class counts are reduced on the spot and Z is never written (except, on request, the final
 // sweep's cube for the reference's `Zs`): sum_j Z goes to a block-wide shared-memory Zin (integer
 // atomics, flushed once per block) and sum_i Z straight to L2 integer atomics, one per non-zero
@@ -198,31 +199,39 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
                 }
             }
 
-            // ---- conditional-binomial chain for the large counts (and the degenerate cells)
-            if (__any_sync(kFull, (nrem | nlast) != 0)) {
+            // ---- conditional-binomial chain for the large counts: classes visited heaviest first
+            // (running argmax of this lane's products; a visited class is marked with -1)
+            if (__any_sync(kFull, nrem > 0)) {
                 double rem = S;
                 U4 w4 = U4{0, 0, 0, 0};
-                for (int k = 0; k <= K - 1; ++k) {
-                    int z = 0;
-                    if (k < K - 1) {
-                        if (!__any_sync(kFull, nrem > 0)) { k = K - 2; continue; }   // jump to the remainder class
-                        if ((k & 3) == 0) w4 = us.words((uint32_t)k >> 2);          // converged: once per four classes
-                        if (nrem > 0) {
-                            const double pk = prob[k * 32 + lane];
-                            if (pk != 0.0) {
-                                const double pp = pk / rem;
-                                const uint32_t wk = (k & 2) ? ((k & 1) ? w4.w : w4.z) : ((k & 1) ? w4.y : w4.x);
-                                z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, k, u32(wk), nrem, pp) : nrem;
-                                nrem -= z;
-                            }
-                            rem = rem - pk;
-                        }
-                    } else {
-                        z = nrem + nlast;
+                for (int t = 0; t < K; ++t) {
+                    if (!__any_sync(kFull, nrem > 0)) break;
+                    double best = -1.0;
+                    int cur = 0;
+                    for (int k = 0; k < K; ++k) {
+                        const double v = prob[k * 32 + lane];
+                        if (v > best) { best = v; cur = k; }
                     }
-                    if (z) z_emit(p, zin_s, row, col, k, z);
+                    prob[cur * 32 + lane] = -1.0;
+                    if (t == K - 1) {                                           // the last class takes the remainder
+                        if (nrem > 0) z_emit(p, zin_s, row, col, cur, nrem);
+                        nrem = 0;
+                        break;
+                    }
+                    if ((t & 3) == 0) w4 = us.words((uint32_t)t >> 2);          // converged: once per four binomials
+                    if (nrem > 0) {
+                        if (best != 0.0) {
+                            const double pp = best / rem;
+                            const uint32_t wt = (t & 2) ? ((t & 1) ? w4.w : w4.z) : ((t & 1) ? w4.y : w4.x);
+                            const int z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, t, u32(wt), nrem, pp) : nrem;
+                            nrem -= z;
+                            if (z) z_emit(p, zin_s, row, col, cur, z);
+                        }
+                        rem = rem - best;
+                    }
                 }
             }
+            if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                // degenerate probabilities
             __syncwarp();
         }
     }
@@ -369,7 +378,7 @@ SG_D void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
     Eo = E;
 }
 
-__global__ void __launch_bounds__(kEThreads) e_family(const EParams p)
+__global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
 {
     __shared__ double E_s[kSeg * kEGroup];                // [128][4]
     const int tid = threadIdx.x, jl = tid & (kSeg - 1), h = tid >> 7;

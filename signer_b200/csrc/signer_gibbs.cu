@@ -85,17 +85,42 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
             w[(size_t)i * d->Jp + j] = wv;
             if (mi > 0) cells.push_back(i + I * j);
         }
-    // z_alloc_fused's work list (a private order: results do not depend on it)
-    std::stable_sort(cells.begin(), cells.end(), [&](int a, int b) {
-        return m[(size_t)(a % I) * d->Jp + a / I] > m[(size_t)(b % I) * d->Jp + b / I];
-    });
+    // z_alloc_fused's work list (a private order: results do not depend on it): counting sort by
+    // count, largest first, ties keep the genome-major order
     d->n_cells = (int)cells.size();
     const size_t nc = std::max<size_t>(cells.size(), 1);
     std::vector<unsigned short> crow(nc, 0);
     std::vector<int> ccol(nc, 0), cn(nc, 0);
-    for (size_t t = 0; t < cells.size(); ++t) {
-        const int i = cells[t] % I, j = cells[t] / I;
-        crow[t] = (unsigned short)i; ccol[t] = j; cn[t] = m[(size_t)i * d->Jp + j];
+    {
+        std::vector<int> cnt(cells.size());
+        int nmax = 0;
+        for (size_t t = 0; t < cells.size(); ++t) {
+            const int i = cells[t] % I, j = cells[t] / I;
+            cnt[t] = m[(size_t)i * d->Jp + j];
+            nmax = std::max(nmax, cnt[t]);
+        }
+        std::vector<size_t> pos;
+        std::vector<int> keys;                       // distinct counts, descending
+        if (nmax <= (1 << 22)) {
+            std::vector<size_t> hist((size_t)nmax + 2, 0);
+            for (int v : cnt) hist[(size_t)v]++;
+            pos.assign((size_t)nmax + 2, 0);
+            size_t run = 0;
+            for (int v = nmax; v >= 1; --v) { pos[(size_t)v] = run; run += hist[(size_t)v]; }
+            for (size_t t = 0; t < cells.size(); ++t) {
+                const size_t dst = pos[(size_t)cnt[t]]++;
+                const int i = cells[t] % I, j = cells[t] / I;
+                crow[dst] = (unsigned short)i; ccol[dst] = j; cn[dst] = cnt[t];
+            }
+        } else {
+            std::vector<size_t> idx(cells.size());
+            for (size_t t = 0; t < idx.size(); ++t) idx[t] = t;
+            std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cnt[a] > cnt[b]; });
+            for (size_t dst = 0; dst < idx.size(); ++dst) {
+                const size_t t = idx[dst];
+                crow[dst] = (unsigned short)(cells[t] % I); ccol[dst] = cells[t] / I; cn[dst] = cnt[t];
+            }
+        }
     }
     CU(cudaMalloc(&d->cell_row, nc * sizeof(unsigned short)));
     CU(cudaMalloc(&d->cell_col, nc * sizeof(int)));
