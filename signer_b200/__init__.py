@@ -4,5 +4,10 @@ include/signer_gibbs.h) is the product; this package is the host-side mirror of 
 R interface for that one path.  No CPU fallback exists."""
 from .gibbs import Chain, GibbsSamplerCpp, SampleList, set_seed   # noqa: F401
 from ._lib import SignerError                                     # noqa: F401
+from .ebayes import eBayesNMF                                     # noqa: F401
+from .estimate import EstimateParameters                          # noqa: F401
+from .signer import Optimal_sigs, signeR                          # noqa: F401
+from .signexp import SignExp                                      # noqa: F401
 
-__all__ = ["GibbsSamplerCpp", "Chain", "SampleList", "SignerError", "set_seed"]
+__all__ = ["GibbsSamplerCpp", "Chain", "SampleList", "SignerError", "set_seed", "eBayesNMF", "EstimateParameters",
+           "Optimal_sigs", "signeR", "SignExp"]
