@@ -1,0 +1,173 @@
+"""CPU tests of the oracle (the checker itself): third-party algorithms against their published
+known answers, the deterministic math against libm/scipy, the samplers against exact laws, and the
+invariants of the model.  'Parity unpinned' (no upstream vectors exist): these are what pins it."""
+import math
+
+import numpy as np
+import pytest
+from scipy import special, stats
+
+from signer_b200 import synth
+
+
+def test_philox_known_answers(oracle):
+    # Random123 kat_vectors, philox4x32-10
+    assert oracle.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_uniform_maps(oracle):
+    L = oracle.lib()
+    assert L.oracle_u53(0, 0) == 2.0 ** -53 and L.oracle_u53(0xffffffff, 0xffffffff) == 1.0 - 2.0 ** -53
+    L.oracle_u32.restype = __import__("ctypes").c_double
+    L.oracle_u32.argtypes = [__import__("ctypes").c_uint32]
+    assert L.oracle_u32(0) == 2.0 ** -33 and L.oracle_u32(0xffffffff) == 1.0 - 2.0 ** -33
+
+
+def test_deterministic_math_accuracy(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([10 ** rng.uniform(-320, 308, 4000), rng.uniform(0.5, 2, 4000), [1.0, 5e-324]])
+    got = np.array([L.oracle_log(v) for v in x]); ref = np.log(x)
+    assert np.max(np.abs(got - ref) / np.spacing(np.abs(ref) + 1e-300)) <= 2.0
+    x = np.concatenate([rng.uniform(-700, 700, 6000), rng.uniform(-1, 1, 2000)])
+    got = np.array([L.oracle_exp(v) for v in x]); ref = np.exp(x)
+    assert np.max(np.abs(got - ref) / np.spacing(ref)) <= 2.0
+    x = np.concatenate([10 ** rng.uniform(-300, 300, 3000), rng.uniform(0, 30, 3000)])
+    got = np.array([L.oracle_lgamma(v) for v in x]); ref = special.gammaln(x)
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 2e-14
+    p = np.concatenate([rng.uniform(0, 1, 4000), 10 ** rng.uniform(-300, -2, 2000)]); p = p[(p > 0) & (p < 1)]
+    got = np.array([L.oracle_ppnd16(v) for v in p]); ref = stats.norm.ppf(p)
+    assert np.max(np.abs(got - ref) / np.maximum(1e-3, np.abs(ref))) < 1e-13
+    assert L.oracle_log(0.0) == -math.inf and math.isnan(L.oracle_log(-1.0)) and L.oracle_exp(-800.0) == 0.0
+    assert L.oracle_exp(800.0) == math.inf and L.oracle_lgamma(0.0) == math.inf
+
+
+@pytest.mark.parametrize("n,p", [(1, 0.3), (20, 0.1), (50, 0.59), (120, 0.2), (200, 0.4), (1000, 0.02), (1000, 0.031),
+                                 (18171, 0.37), (30, 1e-5), (1000, 0.9999)])
+def test_binomial_law(oracle, n, p):
+    """chi-square of the oracle's binomial (inversion below n*min(p,1-p) < 30, BTRS above) against the exact pmf."""
+    L = oracle.lib()
+    N = 12000
+    x = np.array([L.oracle_binomial(7, 3, 1, e, e % 19, n, p) for e in range(N)])
+    assert x.min() >= 0 and x.max() <= n
+    lo = int(max(0, stats.binom.ppf(2e-4, n, p))); hi = int(min(n, stats.binom.ppf(1 - 2e-4, n, p)))
+    if hi <= lo:
+        assert abs(x.mean() - n * p) < 6 * math.sqrt(n * p * (1 - p) / N) + 1e-12
+        return
+    obs = np.array([(x <= lo).sum()] + [(x == k).sum() for k in range(lo + 1, hi)] + [(x >= hi).sum()])
+    pr = np.array([stats.binom.cdf(lo, n, p)] + [stats.binom.pmf(k, n, p) for k in range(lo + 1, hi)] + [stats.binom.sf(hi - 1, n, p)])
+    m = pr * N > 5
+    chi = ((obs[m] - pr[m] * N) ** 2 / (pr[m] * N)).sum() + (obs[~m].sum() - pr[~m].sum() * N) ** 2 / max(pr[~m].sum() * N, 1e-9) * (pr[~m].sum() * N > 1)
+    assert stats.chi2.sf(chi, max(int(m.sum()), 2) - 1) > 1e-4
+
+
+@pytest.mark.parametrize("a,r", [(0.05, 2.0), (0.5, 1.0), (1.0, 3.0), (2.5, 0.5), (30.0, 1e4), (1e4, 1.0)])
+def test_gamma_law(oracle, a, r):
+    L = oracle.lib()
+    g = np.array([L.oracle_gamma(11, 5, 3, e, a, r) for e in range(12000)])
+    assert stats.kstest(g, lambda v: stats.gamma.cdf(v, a, scale=1 / r)).pvalue > 1e-4
+
+
+def test_gamma_clamps_like_reference(oracle):
+    L = oracle.lib()
+    # shape is clamped at 1e-160 (src/gibbs_2.cpp:40): the draw underflows to 0, callers clamp it back to 1e-160
+    assert L.oracle_gamma(1, 0, 6, 0, 0.0, 1.0) == 0.0
+    # scale = max(1e-160, 1/rate) (:41): an infinite rate does not produce 0 or NaN
+    g = L.oracle_gamma(1, 0, 6, 0, 2.0, math.inf)
+    assert 0 < g < 1e-150
+
+
+def test_multinomial_cell_laws_and_invariants(oracle):
+    P = np.array([[0.1, 0.3, 0.0, 0.5, 0.1]]); E = np.array([[2.0], [1.0], [5.0], [0.5], [3.0]])
+    q = P[0] * E[:, 0]; q = q / q.sum()
+    for n in (7, 32, 33, 400):                       # direct method (<= 32) and chain (> 32)
+        N = 4000
+        acc = np.zeros(5)
+        for sw in range(N):
+            z = oracle.multinomial_cell(3, sw, 1, 0, 0, n, P, E)
+            assert z.sum() == n and z[2] == 0 and (z >= 0).all()
+            acc += z
+        chi = ((acc - N * n * q)[q > 0] ** 2 / (N * n * q[q > 0])).sum()
+        assert stats.chi2.sf(chi, 3) > 1e-4, (n, acc / N / n, q)
+    assert oracle.multinomial_cell(3, 0, 1, 0, 0, 0, P, E).sum() == 0
+    assert oracle.multinomial_cell(3, 0, 1, 0, 0, 17.9, P, E).sum() == 17          # truncation like `int size`
+    # K = 1: Z = M ; degenerate probabilities: everything to the last class
+    assert oracle.multinomial_cell(3, 0, 1, 0, 0, 9, np.array([[2.0]]), np.array([[3.0]]))[0] == 9
+    z = oracle.multinomial_cell(3, 0, 1, 0, 0, 9, np.zeros((1, 3)), np.ones((3, 1)))
+    assert list(z) == [0, 0, 9]
+
+
+def test_perm_is_uniform(oracle):
+    cnt = np.zeros((7, 7))
+    for t in range(7000):
+        o = oracle.perm(99, t)
+        assert sorted(o) == [1, 2, 3, 4, 5, 6, 7]
+        for pos, s in enumerate(o):
+            cnt[pos, s - 1] += 1
+    assert stats.chi2.sf(((cnt - 1000) ** 2 / 1000).sum(), 36) > 1e-4
+
+
+def test_chain_invariants_and_loglik(oracle):
+    M, W, _, _ = synth.cohort(20, 33, 3, burden=400.0, seed=3)
+    st = synth.init_state(20, 33, 3, seed=4)
+    r = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=8, eval=4, seed=5)
+    Mi = np.trunc(M)
+    assert np.array_equal(r["Z"].sum(axis=2), Mi)                  # sum_k Z = M in every cell
+    assert np.array_equal(r["Zin"], r["Z"].sum(axis=1)) and np.array_equal(r["Znj"], r["Z"].sum(axis=0).T)
+    assert r["Zin"].sum() == Mi.sum()
+    for k in ("Ps", "Es", "Bps", "Bes", "Aps", "Aes"):
+        assert np.all(np.isfinite(r[k])) and np.all(r[k] > 0)
+    lam = (r["Ps"][:, :, -1] @ r["Es"][:, :, -1]) * W
+    ll = np.sum(Mi * np.log(lam) - special.gammaln(Mi + 1) - lam)       # R/cpp_eBayesNMF.R:181-185
+    assert abs(r["loglik"][-1] - ll) <= 1e-10 * abs(ll)
+    assert np.allclose(r["bic"], 2 * r["loglik"] - 3 * (20 + 33) * math.log(33), rtol=1e-14)
+    # the last sample slices are the final state (what R re-reads, R/cpp_eBayesNMF.R:115-139)
+    assert np.array_equal(r["Ps"][:, :, -1], r["P"]) and np.array_equal(r["Es"][:, :, -1], r["E"])
+
+
+def test_pfixed_and_forced_order(oracle):
+    M, W, cosmic = synth.breast21()
+    st = synth.init_state(96, 21, 6, seed=3, fixedP=cosmic)
+    r = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=3, eval=2, Pfixed=True, seed=1)
+    assert np.array_equal(r["P"], cosmic) and not r["Bp"].any() and not r["Ap"].any()
+    # an empty forced order leaves the state untouched
+    r2 = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=0, eval=1, seed=1,
+                          forced_order=[0] * 7)
+    assert np.array_equal(r2["E"], st["E"]) and np.array_equal(r2["Ae"], st["Ae"])
+
+
+def test_conjugate_step_moments(oracle):
+    """Known answer from conjugacy: one step-2 draw of P has mean (Ap+1+Zin)/(Bp+W E')."""
+    M, W, _, _ = synth.cohort(96, 60, 3, burden=3000.0, seed=8)
+    st = synth.init_state(96, 60, 3, seed=9)
+    Z = np.zeros((96, 60, 3), order="F"); Z[:, :, 1] = np.trunc(M)
+    zs = []
+    for seed in range(30):
+        r = oracle.gibbs_run(M, W, Z, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=0, eval=1, seed=seed,
+                             forced_order=[2, 0, 0, 0, 0, 0, 0])
+        shape = st["Ap"] + 1 + Z.sum(axis=1); rate = st["Bp"] + W @ st["E"].T
+        zs.append((r["P"] - shape / rate) / (np.sqrt(shape) / rate))
+    zs = np.array(zs)
+    assert abs(zs.mean()) < 5 / math.sqrt(zs.size) and abs(zs.var() - 1) < 0.05
+
+
+def test_host_mirror_pieces_cpu(sg):
+    from signer_b200.signexp import SignExp, _fivenum_whiskers
+    from signer_b200.estimate import EstimateParameters
+    assert np.allclose(_fivenum_whiskers(np.array([[1., 2, 3, 4, 5, 6, 7, 8, 9, 100]])), [[1, 3, 5.5, 8, 9]])
+    rng = np.random.default_rng(0)
+    a, b, l = EstimateParameters(rng.exponential(1 / 1.436, 100000), rng.gamma(2.0506, 1 / 1.325, 100000), 1, 1)
+    assert abs(a - 2.0506) < 0.05 and abs(b - 1.325) < 0.04 and abs(l - 1.436) < 0.03
+    Ps = rng.gamma(2, 1, (10, 3, 7)); Es = rng.gamma(2, 1, (3, 5, 7))
+    SE = SignExp(Ps, Es)
+    assert np.allclose(SE.Sign.sum(axis=0), 1.0)                                # R/Definition_SignExp_object.R:120
+    assert np.allclose(np.einsum("ikr,kjr->ijr", SE.Sign, SE.Exp), np.einsum("ikr,kjr->ijr", Ps, Es))
+    assert np.allclose(SE.median_exp(), np.median(SE.Exp, axis=2))
+    # the selection rule on a synthetic BIC curve peaked at 5, ties to the smaller n
+    tf = lambda n: [np.full(9, -(n - 5) ** 2 + 0.0), None]
+    assert sg.Optimal_sigs(tf, 2, 10, 2)[0] == 5 and sg.Optimal_sigs(tf, 2, 40, 8)[0] == 5
+    flat = lambda n: [np.zeros(9), None]
+    assert sg.Optimal_sigs(flat, 2, 10, 2)[0] == 2
