@@ -256,7 +256,7 @@ def main():
 
     # ---------------- evaluation sweeps (samples + log-likelihood kept on the device)
     n_eval = min(args.steps, 500)
-    chain.run(eval=8, fetch=False)
+    chain.run(eval=n_eval, keep_par=False, fetch=False)      # warm-up: also sizes the device rings
     barrier()
     e0.record(stream)
     chain.run(eval=n_eval, keep_par=False, fetch=False)

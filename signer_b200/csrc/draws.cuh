@@ -137,7 +137,7 @@ SG_D double det_exp(double x)
 }
 
 // lgamma for x > 0: recurrence up to y >= 8, then 8 Stirling terms.
-SG_D double det_lgamma(double x)
+__device__ __noinline__ double det_lgamma(double x)
 {
     if (x != x) return x;
     if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
@@ -297,7 +297,7 @@ SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double
 
 // ---------------------------------------------------------------- gamma (Marsaglia & Tsang 2000)
 // Gamma(shape, rate) with one_gamma_dist's clamps (src/gibbs_2.cpp:39-43).  Attempt t reads block t.
-SG_D double gamma_draw(const UStream &s, double shape, double rate)
+__device__ __noinline__ double gamma_draw(const UStream &s, double shape, double rate)
 {
     const double a = (kTiny < shape) ? shape : kTiny;
     const double invr = 1.0 / rate;

@@ -258,7 +258,7 @@ SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, doubl
 }
 
 // steps 6/7 (src/gibbs_2.cpp:172-251): gamma proposal, log acceptance ratio, uniform accept
-SG_D double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var)
+__device__ __noinline__ double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var)
 {
     UStream us; us.init(key, sweep, stream, e);
     const double shape = (A * A) / var;
@@ -355,7 +355,7 @@ struct EParams {
 
 constexpr int kEGroup = 4;      // classes per block
 
-SG_D void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
+__device__ __noinline__ void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
 {
     double E = p.E[e], Ae = p.Ae[e], Be = p.Be[e];
     for (int o = 0; o < p.ops.n; ++o) {
@@ -450,12 +450,15 @@ struct LLParams {
 
 __global__ void __launch_bounds__(128) loglik_cols(const LLParams p)
 {
+    // 32 genomes per block.  The terms of a 32-row chunk are evaluated by all 128 threads (8 rows each)
+    // into shared memory, then one thread per genome adds them in row order, chunk after chunk.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int I = p.I, J = p.J, K = p.K;
     const int nchunk = (I + kLLChunk - 1) / kLLChunk;
     double *E_s = reinterpret_cast<double *>(smem_raw);   // [K][33]
-    double *part = E_s + K * 33;                          // [nchunk][32]
-    const int tid = threadIdx.x, lane = tid & 31, cl = tid >> 5;
+    double *P_s = E_s + K * 33;                           // [32][K]
+    double *term = P_s + kLLChunk * K;                    // [32][33]
+    const int tid = threadIdx.x, lane = tid & 31, rl = tid >> 5;
     const int j0 = blockIdx.x * 32, j = j0 + lane;
     if (p.mode == 0) {
         for (int idx = tid; idx < K * 32; idx += 128) {
@@ -463,41 +466,61 @@ __global__ void __launch_bounds__(128) loglik_cols(const LLParams p)
             E_s[k * 33 + jj] = (j0 + jj < J) ? p.E[(size_t)K * j0 + idx] : 0.0;
         }
     }
-    __syncthreads();
-    for (int c = cl; c < nchunk; c += 4) {
-        double a = 0.0;
-        if (j < J) {
-            const int i1 = min(I, (c + 1) * kLLChunk);
-            for (int i = c * kLLChunk; i < i1; ++i) {
+    double a = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+        const int i0 = c * kLLChunk, rows = min(kLLChunk, I - i0);
+        __syncthreads();
+        if (p.mode == 0)
+            for (int idx = tid; idx < kLLChunk * K; idx += 128) {
+                const int r = idx & 31, k = idx >> 5;
+                P_s[r * K + k] = (r < rows) ? p.P[(size_t)(i0 + r) + (size_t)I * k] : 0.0;
+            }
+        __syncthreads();
+        for (int rr = 0; rr < 8; ++rr) {
+            const int r = rl * 8 + rr, i = i0 + r;
+            double t = 0.0;
+            if (r < rows && j < J) {
                 const double m = (double)p.M[(size_t)i * p.Jp + j];
                 if (p.mode == 0) {
+                    const double *Pr = P_s + r * K;
                     double pe = 0.0;
-                    for (int k = 0; k < K; ++k) pe = fma(__ldg(p.P + (size_t)i + (size_t)I * k), E_s[k * 33 + lane], pe);
+                    for (int k = 0; k < K; ++k) pe = fma(Pr[k], E_s[k * 33 + lane], pe);
                     const double lam = pe * p.W[(size_t)i * p.Jp + j];
-                    a = a + (m * det_log(lam) - lam);
+                    t = m * det_log(lam) - lam;
                 } else {
-                    a = a + det_lgamma(m + 1.0);
+                    t = det_lgamma(m + 1.0);
                 }
             }
+            term[r * 33 + lane] = t;
         }
-        part[c * 32 + lane] = a;
+        __syncthreads();
+        if (tid < 32) {
+            double ac = 0.0;
+            for (int r = 0; r < rows; ++r) ac = ac + term[r * 33 + tid];
+            a = a + ac;
+        }
     }
-    __syncthreads();
-    if (tid < 32 && j < J) {
-        double a = 0.0;
-        for (int c = 0; c < nchunk; ++c) a = a + part[c * 32 + tid];
-        p.col[j] = a;
-    }
+    if (tid < 32 && j < J) p.col[j] = a;
 }
 
-// a[t] += a[t+s] for s = n2/2 .. 1 ; result written to out[0] = a[0] - sub (sub may be null)
+// a[t] += a[t+s] for s = n2/2 .. 1 ; result written to out[0] = a[0] - sub (sub may be null).
+// The last levels (s < 2048) run in shared memory; the arithmetic is the same.
 __global__ void __launch_bounds__(1024) tree_sum(double *a, int n2, const double *sub, double *out)
 {
-    for (int s = n2 >> 1; s >= 1; s >>= 1) {
+    __shared__ double sh[4096];
+    int s = n2 >> 1;
+    for (; s >= 4096; s >>= 1) {
         for (int t = threadIdx.x; t < s; t += 1024) a[t] = a[t] + a[t + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = sub ? a[0] - sub[0] : a[0];
+    const int m = min(n2, 4096);
+    for (int t = threadIdx.x; t < m; t += 1024) sh[t] = a[t];
+    __syncthreads();
+    for (s = m >> 1; s >= 1; s >>= 1) {
+        for (int t = threadIdx.x; t < s; t += 1024) sh[t] = sh[t] + sh[t + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sub ? sh[0] - sub[0] : sh[0];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -43,7 +44,7 @@ int fail(int code, const std::string &msg)
         if (s_ != SIGNER_OK) return s_;           \
     } while (0)
 
-constexpr size_t kRingBytes = size_t(3) << 30;   // per ring set (two sets)
+constexpr size_t kRingBytes = size_t(256) << 20;   // per ring set (two sets): small enough to pipeline D2H behind compute
 
 // The data of one cohort on one device, shared by every chain on that device.
 struct DeviceData {
@@ -139,7 +140,8 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
     CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
     LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1};
     const int nchunk = (I + kLLChunk - 1) / kLLChunk;
-    const size_t smem = sizeof(double) * (size_t)(33 + nchunk * 32);
+    (void)nchunk;
+    const size_t smem = sizeof(double) * (size_t)(1 * 33 + kLLChunk * 1 + kLLChunk * 33);
     loglik_cols<<<(J + 31) / 32, 128, smem>>>(lp);
     tree_sum<<<1, 1024>>>(col, d->n2, nullptr, d->lgm);
     CU(cudaGetLastError());
@@ -304,8 +306,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
 int launch_loglik(signer_chain *c, double *out)
 {
     LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col, 0};
-    const int nchunk = (c->I + kLLChunk - 1) / kLLChunk;
-    const size_t smem = sizeof(double) * (size_t)(c->K * 33 + nchunk * 32);
+    const size_t smem = sizeof(double) * (size_t)(c->K * 33 + kLLChunk * c->K + kLLChunk * 33);
     {
         ProfScope ps(c, 3);
         loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
@@ -314,6 +315,17 @@ int launch_loglik(signer_chain *c, double *out)
     c->launches += 2;
     CU(cudaGetLastError());
     return SIGNER_OK;
+}
+
+// Touch every page of a caller-allocated output buffer (it is ours to overwrite) so that the later
+// device-to-host copies land on resident pages; runs on helper threads while the GPU does the burn-in.
+void prefault(double *p, size_t n_doubles)
+{
+    if (!p) return;
+    volatile char *b = reinterpret_cast<volatile char *>(p);
+    const size_t bytes = n_doubles * sizeof(double);
+    for (size_t off = 0; off < bytes; off += 4096) b[off] = 0;
+    if (bytes) b[bytes - 1] = 0;
 }
 
 struct Slots { double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr; };
@@ -524,6 +536,16 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     }
     const int total = burn + eval, cap = std::max(1, c->ring_cap);
     int chunk_r0 = 0;
+    std::vector<std::thread> faulters;
+    auto join_faulters = [&]() { for (auto &t : faulters) if (t.joinable()) t.join(); faulters.clear(); };
+    if (out && eval > 0) {
+        const size_t R = (size_t)eval;
+        double *bufs[7] = {out->Es, out->Bes, keep_par ? out->Aes : nullptr, out->Ps, out->Bps, keep_par ? out->Aps : nullptr, zcube ? out->Zs : nullptr};
+        const size_t lens[7] = {c->nE * R, c->nE * R, c->nE * R, c->nP * R, c->nP * R, c->nP * R, (size_t)c->I * c->J * c->K};
+        for (int b = 0; b < 7; ++b)
+            if (bufs[b] && lens[b] * sizeof(double) >= (size_t(8) << 20)) faulters.emplace_back(prefault, bufs[b], lens[b]);
+    }
+    struct Joiner { std::function<void()> f; ~Joiner() { f(); } } joiner{join_faulters};
     for (int k = 0; k < total; ++k) {
         const uint32_t sweep = c->sweep0 + (uint32_t)c->sweeps_done;
         int order[7];
@@ -547,6 +569,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             if (slot == cap - 1 || last) {
                 CU(cudaEventRecord(rg.filled, c->stream));
                 if (out) {
+                    join_faulters();
                     if (chunk >= 1) ST(flush_chunk(c, chunk - 1, chunk_r0 - cap, cap, keep_par, out));
                     if (last) ST(flush_chunk(c, chunk, chunk_r0, slot + 1, keep_par, out));
                 }
@@ -559,6 +582,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     if (out && eval > 0) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
+        join_faulters();
         if (zcube && out->Zs) {
             // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined
             CU(cudaMemcpy(out->Zs, zcube, sizeof(double) * (size_t)c->I * c->J * c->K, cudaMemcpyDeviceToHost));
