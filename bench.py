@@ -178,6 +178,47 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_nsig(args):
+    """Secondary metric: wall time of the nsig model-selection sweep (every candidate n in the range x
+    `chains` chains, testing_burn = testing_eval = 1000 as R/signeR.R:66) on N GPUs, one process per GPU,
+    candidates dealt longest-first over the ranks; only BIC vectors travel."""
+    import torch
+    from signer_b200 import dist, synth
+    from signer_b200.signer import batch_bics
+    rank, world, local = dist.init()
+    wl = args.workload if args.workload != "cfg3_96x10000_K20" else "cfg2_96x560"
+    M, W, _, _ = synth.named(wl)
+    I, J = M.shape
+    lo, hi = (int(x) for x in args.nsig_range.split(","))
+    h0 = synth.hyper_tuple()
+    tasks = []
+    for n in range(lo, hi + 1):
+        for c in range(args.chains):
+            h = list(h0); h[3] = h0[3] / np.sqrt(n)                     # be/sqrt(n), R/signeR.R:163
+            tasks.append(dict(K=n, state=synth.init_state(I, J, n, hyper=dict(be=h[3]), seed=1000 * n + c), hyper=tuple(h),
+                              burn=1000, eval=1000, seed=1000 * n + c))
+
+    def runner(ts):
+        return batch_bics(M, W, ts, devices=[local]) if ts else []
+    runner(tasks[:1])                                                    # warm-up (context, module load)
+    dist.barrier()
+    t0 = time.perf_counter()
+    res = dist.run_tasks_distributed(tasks, runner)
+    dist.barrier()
+    dt = dist.max_over_ranks(time.perf_counter() - t0)
+    if rank == 0:
+        med = {}
+        for tk, (ll, bic) in zip(tasks, res):
+            med.setdefault(tk["K"], []).append(float(np.median(bic)))
+        med = {k: float(np.mean(v)) for k, v in med.items()}
+        best = max(sorted(med), key=lambda k: med[k])
+        print(json.dumps(dict(metric="nsig_sweep_wall_s", value=dt, unit="s", n_gpus=world, higher_is_better=False, scaling="strong",
+                              config=dict(workload=wl, I=I, J=J, nsig=[lo, hi], chains=args.chains, burn=1000, eval=1000, tasks=len(tasks)),
+                              bic_optimal_nsig=best, median_bic=med, sweeps_per_s=sum(t["burn"] + t["eval"] for t in tasks) / dt)), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +228,10 @@ def main():
     ap.add_argument("--workload", default="cfg3_96x10000_K20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="sweeps", choices=["sweeps", "nsig"],
+                    help="nsig: wall time of a full nsig model-selection sweep (secondary metric of BASELINE.json)")
+    ap.add_argument("--nsig-range", default="2,10")
+    ap.add_argument("--chains", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -196,6 +241,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.mode == "nsig":
+        run_nsig(args)
         return
 
     import torch
