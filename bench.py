@@ -31,6 +31,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "NONE")      # keep stdout to the one JSON line (no NCCL version banner)
 
 METRIC = "gibbs_sweeps_per_s"
 UNIT = "sweeps/s"
@@ -249,28 +250,15 @@ def main():
     import torch
     import torch.distributed as dist
     import signer_b200 as sg
-    from signer_b200 import synth
+    from signer_b200 import dist as sgdist, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    sgdist.init("nccl")
     dist_on = world > 1
-    if dist_on:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist_on:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if not dist_on:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier = sgdist.barrier
+    max_over_ranks = sgdist.max_over_ranks
 
     wl = WORKLOADS[args.workload]
     K = wl["K"]

@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -148,6 +149,21 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
     CU(cudaDeviceSynchronize());
     CU(cudaFree(col));
     out = d;
+    return SIGNER_OK;
+}
+
+// z_alloc_fused may need more than 48 KB of dynamic shared memory; raise the limit once per device to the
+// architectural maximum so that concurrent chains with different K never race on the attribute.
+int ensure_device_setup(int device)
+{
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) return fail(SIGNER_ERR_ARG, "device ordinal out of range");
+    if (done[device]) return SIGNER_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    done[device] = true;
     return SIGNER_OK;
 }
 
@@ -481,7 +497,8 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->z_warp_smem = (int)z_smem_bytes_per_warp(K);
     c->z_zin_smem = (c->nP * sizeof(int) <= (size_t)kZinSmemMax) ? 1 : 0;
     const size_t zsm = (size_t)c->z_warp_smem * kZWarps + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
-    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+    if (zsm > (size_t)226 * 1024) return fail(SIGNER_ERR_ARG, "z_alloc_fused: K too large for shared memory");
+    ST(ensure_device_setup(c->device));
     int occ = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * kZWarps, zsm));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
@@ -739,27 +756,43 @@ int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W, s
     }
     std::vector<std::string> errs(n_devices);
     std::vector<int> rcs(n_devices, SIGNER_OK);
+    // small cohorts are launch-latency bound: run several chains per device concurrently (own streams)
+    const long long cells = (long long)I * J;
+    const int tpd = cells <= 250000 ? 4 : (cells <= 2000000 ? 2 : 1);
+    std::vector<std::shared_ptr<DeviceData>> datas(n_devices);
+    std::vector<std::atomic<int>> next(n_devices);
+    std::vector<std::mutex> mus(n_devices);
+    for (int d = 0; d < n_devices; ++d) {
+        next[d] = 0;
+        if (mine[d].empty()) continue;
+        const int rc = upload_data(devices[d], I, J, M, W, datas[d]);
+        if (rc != SIGNER_OK) { rcs[d] = rc; errs[d] = g_err; for (int t : mine[d]) tasks[t].status = rc; mine[d].clear(); }
+    }
     std::vector<std::thread> th;
     for (int d = 0; d < n_devices; ++d) {
-        th.emplace_back([&, d]() {
-            if (mine[d].empty()) return;
-            std::shared_ptr<DeviceData> data;
-            int rc = upload_data(devices[d], I, J, M, W, data);
-            if (rc != SIGNER_OK) { rcs[d] = rc; errs[d] = g_err; for (int t : mine[d]) tasks[t].status = rc; return; }
-            for (int t : mine[d]) {
-                signer_task &tk = tasks[t];
-                signer_chain *c = nullptr;
-                rc = chain_create(data, tk.K, &tk.state, &tk.opts, &c);
-                if (rc == SIGNER_OK) {
-                    signer_outputs out{};
-                    out.loglik = tk.loglik; out.bic = tk.bic;
-                    rc = chain_run(c, tk.opts.burn, tk.opts.eval, 0, tk.opts.forced_order, &out);
+        const int nth = std::min<int>(tpd, (int)mine[d].size());
+        for (int w = 0; w < nth; ++w) {
+            th.emplace_back([&, d]() {
+                for (;;) {
+                    const int q = next[d].fetch_add(1);
+                    if (q >= (int)mine[d].size()) break;
+                    signer_task &tk = tasks[mine[d][q]];
+                    signer_chain *c = nullptr;
+                    int rc = chain_create(datas[d], tk.K, &tk.state, &tk.opts, &c);
+                    if (rc == SIGNER_OK) {
+                        signer_outputs out{};
+                        out.loglik = tk.loglik; out.bic = tk.bic;
+                        rc = chain_run(c, tk.opts.burn, tk.opts.eval, 0, tk.opts.forced_order, &out);
+                    }
+                    delete c;
+                    tk.status = rc;
+                    if (rc != SIGNER_OK) {
+                        std::lock_guard<std::mutex> lk(mus[d]);
+                        if (rcs[d] == SIGNER_OK) { rcs[d] = rc; errs[d] = g_err; }
+                    }
                 }
-                delete c;
-                tk.status = rc;
-                if (rc != SIGNER_OK && rcs[d] == SIGNER_OK) { rcs[d] = rc; errs[d] = g_err; }
-            }
-        });
+            });
+        }
     }
     for (auto &t : th) t.join();
     for (int d = 0; d < n_devices; ++d)

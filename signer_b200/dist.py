@@ -11,6 +11,25 @@ def env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0")))
 
 
+import contextlib
+import sys
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """NCCL prints its version banner on stdout when the first communicator is created; callers
+    that promise ONE line of JSON on stdout wrap communicator creation in this."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def init(backend=None):
     """Initialise torch.distributed from the torchrun environment (nccl on GPUs, gloo on CPU)."""
     import torch
@@ -25,7 +44,9 @@ def init(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
-        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+        with stdout_to_stderr():
+            dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+            dist.barrier()                              # creates the communicator (and its banner) now
     return rank, world, local
 
 
