@@ -336,11 +336,8 @@ int oracle_binomial(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t ele
 
 /* Gamma(shape, rate) with the clamps of one_gamma_dist (src/gibbs_2.cpp:39-43);
  * Marsaglia & Tsang, "A simple method for generating gamma variables" (ACM TOMS 26, 2000). */
-static double gamma_draw(const ustream *s, double shape, double rate)
+static double gamma_core(const ustream *s, double a, double scale)
 {
-    double a = (TINY < shape) ? shape : TINY;
-    double invr = 1.0 / rate;
-    double scale = (TINY < invr) ? invr : TINY;
     int boost = a < 1.0;
     double aa = boost ? a + 1.0 : a;
     double d = aa - 1.0 / 3.0;
@@ -364,6 +361,30 @@ static double gamma_draw(const ustream *s, double shape, double rate)
         g = g * oracle_exp(oracle_log(ub) / a);
     }
     return g * scale;
+}
+
+static double gamma_draw(const ustream *s, double shape, double rate)
+{
+    double a = (TINY < shape) ? shape : TINY;             /* one_gamma_dist, src/gibbs_2.cpp:40-41 */
+    double invr = 1.0 / rate;
+    double scale = (TINY < invr) ? invr : TINY;
+    return gamma_core(s, a, scale);
+}
+
+/* the R::rgamma(shape, scale) the reference calls after its own clamps (src/gibbs_2.cpp:42) */
+double oracle_rgamma(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem, double shape, double scale)
+{
+    ustream s; us_init(&s, seed, sweep, stream, elem);
+    return gamma_core(&s, shape, scale);
+}
+
+/* the MH acceptance uniform of an element (second half of the auxiliary block) */
+double oracle_mh_uniform(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem)
+{
+    ustream s; us_init(&s, seed, sweep, stream, elem);
+    double ub, um;
+    us_block(&s, AUX_BLOCK, &ub, &um);
+    return um;
 }
 
 double oracle_gamma(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem, double shape, double rate)

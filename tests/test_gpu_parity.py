@@ -168,3 +168,22 @@ def test_errors(sg):
     assert e.value.code == 6
     with pytest.raises(ValueError):
         sg.GibbsSamplerCpp(M, W[:, :-1], None, *args, False, False, False, False, True)
+
+
+def test_cuda_equals_reference_source(sg, oracle):
+    """The CUDA path against the reference's own src/gibbs_2.cpp (oracle/_ref, built from /root/reference in the
+    dev container with the draw specification standing in for R nmath / Armadillo RNG)."""
+    ref_runner = pytest.importorskip("oracle.ref_runner")
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref not built")
+    M, W, _ = synth.breast21()
+    st = synth.init_state(96, 21, 5, seed=31)
+    h = synth.hyper_tuple()
+    Z0 = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=0, eval=0, seed=17)["Z"]
+    got = sg.GibbsSamplerCpp(M, W, Z0, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *h, 15, 6,
+                             False, False, False, False, True, seed=17)
+    ref = ref_runner.gibbs_run(M, W, Z0, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], burn=15, eval=6, seed=17)
+    assert ref["list_shape_ok"]
+    for slot, k in ((2, "Ps"), (3, "Es"), (4, "Aps"), (5, "Bps"), (6, "Aes"), (7, "Bes")):
+        assert_bits_equal(got[slot], ref[k], k)
+    assert_bits_equal(got[0][:, :, :, 0], ref["Z"], "Zs")
