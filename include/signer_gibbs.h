@@ -138,6 +138,16 @@ int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W,
                        signer_task *tasks, int32_t n_tasks,
                        const int32_t *devices, int32_t n_devices);
 
+/* One chain over several GPUs, the genome columns sharded in 128-genome segments (very wide cohorts, BASELINE.json
+ * config 4).  P, Ap, Bp are replicated; per sweep the shards exchange two sets of I*K values (NCCL all-reduce over
+ * NVLink): the integer sums over genomes of Z and their ordered W E' sums.  Same arguments and outputs as
+ * signer_gibbs_run (opts.device ignored).  devices: n_devices distinct CUDA ordinals, or the same ordinal repeated
+ * (shards emulated on one GPU, for tests).  Results are identical for both placements and equal the oracle run with
+ * nshards = n_devices; they differ from the unsharded run only in the rounding of W E' (a different, still fixed,
+ * summation order). */
+int signer_gibbs_run_sharded(const signer_problem *problem, const signer_state *state, const signer_opts *opts,
+                             signer_outputs *out, const int32_t *devices, int32_t n_devices);
+
 /* Test hooks: the deterministic primitives of the draw specification evaluated ON THE DEVICE, so
  * tests can compare them bit for bit with the oracle.  n values each; fn: 0 log, 1 exp, 2 lgamma,
  * 3 ppnd16. */

@@ -53,7 +53,7 @@ class Task(C.Structure):
 
 
 EXPORTS = [
-    "signer_gibbs_run", "signer_chain_create", "signer_chain_set_stream", "signer_chain_set_hyper",
+    "signer_gibbs_run", "signer_gibbs_run_sharded", "signer_chain_create", "signer_chain_set_stream", "signer_chain_set_hyper",
     "signer_chain_run", "signer_chain_sync", "signer_chain_fetch_state", "signer_chain_fetch_stats",
     "signer_chain_profile", "signer_chain_sweeps", "signer_chain_launches", "signer_chain_destroy", "signer_gibbs_batch",
     "signer_test_math", "signer_test_binomial", "signer_test_gamma", "signer_test_perm",
@@ -75,6 +75,8 @@ def lib():
     vp = C.c_void_p
     L.signer_gibbs_run.restype = C.c_int
     L.signer_gibbs_run.argtypes = [C.POINTER(Problem), C.POINTER(State), C.POINTER(Opts), C.POINTER(Outputs)]
+    L.signer_gibbs_run_sharded.restype = C.c_int
+    L.signer_gibbs_run_sharded.argtypes = [C.POINTER(Problem), C.POINTER(State), C.POINTER(Opts), C.POINTER(Outputs), ip, C.c_int32]
     L.signer_chain_create.restype = C.c_int
     L.signer_chain_create.argtypes = [C.POINTER(Problem), C.POINTER(State), C.POINTER(Opts), C.POINTER(vp)]
     L.signer_chain_set_stream.restype = C.c_int

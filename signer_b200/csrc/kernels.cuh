@@ -52,6 +52,7 @@ constexpr int kZinSmemMax = 40 * 1024;
 
 struct ZParams {
     int I, J, K;
+    int col0, Jglobal;                // column shard: first global genome of this shard, genomes in the whole cohort
     const unsigned short *cell_row;   // [n_cells] context of each listed cell
     const int *cell_col;              // [n_cells] genome
     const int *cell_n;                // [n_cells] count, non-increasing
@@ -80,7 +81,7 @@ SG_D void z_emit(const ZParams &p, int *zin_s, int row, int col, int k, int z)
     if (zin_s) atomicAdd(zin_s + row + p.I * k, z);
     else atomicAdd(p.Zin + (size_t)row + (size_t)p.I * k, z);
     atomicAdd(p.Znj + (size_t)k + (size_t)p.K * col, z);
-    if (p.Zcube) p.Zcube[(size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k)] = (double)z;
+    if (p.Zcube) p.Zcube[(size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k)] = (double)z;     // the shard's own cube
 }
 
 __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p)
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
             int nrem = (valid && ok && n > kNDirect) ? n : 0;
             const int nlast = (valid && !ok) ? n : 0;       // degenerate probabilities: all to the last class
             UStream us;
-            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * col));
+            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * (col + p.col0)));
 
             // ---- direct method
             if (__any_sync(kFull, small)) {
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
 // ------------------------------------------------------------------------------------------------
 struct EParams {
     int I, J, Jp, K;
+    int col0;                   // column shard: first global genome (random streams are addressed globally)
     const double *W;            // [I][Jp]
     const double *P;
     double *E, *Ae, *Be;
@@ -358,17 +360,18 @@ constexpr int kEGroup = 4;      // classes per block
 __device__ __noinline__ void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
 {
     double E = p.E[e], Ae = p.Ae[e], Be = p.Be[e];
+    const uint32_t eg = (uint32_t)(e + (size_t)p.K * p.col0);        // global element k + K*j of the streams
     for (int o = 0; o < p.ops.n; ++o) {
         const int op = p.ops.get(o);
         if (op == 3) {
-            UStream us; us.init(p.key, p.sweep, kStE, (uint32_t)e);
+            UStream us; us.init(p.key, p.sweep, kStE, eg);
             const double shape = Ae + 1 + (double)p.Znj[e];
             const double rate = Be + corrP;
             E = gamma_draw(us, shape, rate);
         } else if (op == 5) {
-            Be = update_b(p.key, p.sweep, kStBe, (uint32_t)e, Ae, E, p.h.ae, p.h.be);
+            Be = update_b(p.key, p.sweep, kStBe, eg, Ae, E, p.h.ae, p.h.be);
         } else if (op == 7) {
-            Ae = update_a(p.key, p.sweep, kStAe, (uint32_t)e, Ae, E, Be, p.h.le, p.h.var_ae);
+            Ae = update_a(p.key, p.sweep, kStAe, eg, Ae, E, Be, p.h.le, p.h.var_ae);
         }
     }
     p.E[e] = E; p.Ae[e] = Ae; p.Be[e] = Be;
@@ -551,6 +554,29 @@ __global__ void stats_reduce(const double *a, const double *b, size_t n, double 
         sa += __shfl_xor_sync(kFull, sa, o); sb += __shfl_xor_sync(kFull, sb, o); sl += __shfl_xor_sync(kFull, sl, o);
     }
     if ((threadIdx.x & 31) == 0) { atomicAdd(out, sa); atomicAdd(out + 1, sb); atomicAdd(out + 2, sl); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sharding: a shard adds its own W E' segment partials in order into its slot of the gathered
+// buffer (the other slots stay zero, so the all-reduce over shards is exact in any order)
+// ------------------------------------------------------------------------------------------------
+__global__ void seg_reduce(const double *part, int n_seg, int IK, double *out_slot)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= IK) return;
+    double acc = 0.0;
+    for (int s = 0; s < n_seg; ++s) acc = acc + part[(size_t)s * IK + e];
+    out_slot[e] = acc;
+}
+// same-device emulation of the all-reduce (shards sharing one GPU, for tests): every buffer <- sum of all
+template <typename T>
+__global__ void sum_shards(T *const *bufs, int n_shards, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        T acc = bufs[0][i];
+        for (int g = 1; g < n_shards; ++g) acc = acc + bufs[g][i];
+        for (int g = 0; g < n_shards; ++g) bufs[g][i] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

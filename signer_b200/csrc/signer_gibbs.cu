@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -50,6 +51,7 @@ constexpr size_t kRingBytes = size_t(256) << 20;   // per ring set (two sets): s
 // The data of one cohort on one device, shared by every chain on that device.
 struct DeviceData {
     int device = 0, I = 0, J = 0, Jp = 0, n2 = 0;
+    int col0 = 0, Jglobal = 0;  // column shard: first global genome, genomes in the whole cohort
     // z_alloc's work list: the non-zero cells sorted by count (largest first, ties genome-major)
     unsigned short *cell_row = nullptr;
     int *cell_col = nullptr, *cell_n = nullptr;
@@ -64,14 +66,17 @@ struct DeviceData {
     }
 };
 
-int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out)
+int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out, int col0 = 0,
+                int Jglobal = -1)
 {
+    if (Jglobal < 0) Jglobal = J;
     if (I <= 0 || J <= 0 || !M || !W) return fail(SIGNER_ERR_ARG, "problem: I, J must be positive and M, W non-null");
     if ((long long)I * J >= (1LL << 31)) return fail(SIGNER_ERR_ARG, "problem: I*J must be below 2^31");
     CU(cudaSetDevice(device));
     auto d = std::make_shared<DeviceData>();
     d->device = device; d->I = I; d->J = J; d->Jp = (J + 31) / 32 * 32;
-    d->n2 = 1; while (d->n2 < J) d->n2 <<= 1;
+    d->col0 = col0; d->Jglobal = Jglobal;
+    d->n2 = 1; while (d->n2 < Jglobal) d->n2 <<= 1;
     if (I > 65535) return fail(SIGNER_ERR_ARG, "problem: I must be below 65536");
     const size_t n = (size_t)I * d->Jp;
     std::vector<int> m(n, 0);
@@ -135,19 +140,19 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
     CU(cudaMemcpy(d->cell_n, cn.data(), nc * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d->Mrow, m.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d->W, w.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-    // constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180)
-    double *col = nullptr;
-    CU(cudaMalloc(&col, (size_t)d->n2 * sizeof(double)));
-    CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
-    LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1};
-    const int nchunk = (I + kLLChunk - 1) / kLLChunk;
-    (void)nchunk;
-    const size_t smem = sizeof(double) * (size_t)(1 * 33 + kLLChunk * 1 + kLLChunk * 33);
-    loglik_cols<<<(J + 31) / 32, 128, smem>>>(lp);
-    tree_sum<<<1, 1024>>>(col, d->n2, nullptr, d->lgm);
-    CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    CU(cudaFree(col));
+    // constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180); a column shard computes it with its peers
+    if (Jglobal == J) {
+        double *col = nullptr;
+        CU(cudaMalloc(&col, (size_t)d->n2 * sizeof(double)));
+        CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
+        LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1};
+        const size_t smem = sizeof(double) * (size_t)(1 * 33 + kLLChunk * 1 + kLLChunk * 33);
+        loglik_cols<<<(J + 31) / 32, 128, smem>>>(lp);
+        tree_sum<<<1, 1024>>>(col, d->n2, nullptr, d->lgm);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(col));
+    }
     out = d;
     return SIGNER_OK;
 }
@@ -183,6 +188,8 @@ struct signer_chain {
     int zcur = 0;
     double *corrE_part = nullptr;
     int n_seg = 0;
+    int shard = 0, n_shards = 1, col0 = 0;   // column sharding (signer_gibbs_run_sharded)
+    double *corrE_all = nullptr;             // [n_shards][I*K]: every shard's ordered W E' sum, after the all-reduce
     double *col = nullptr, *ll_ring = nullptr;
     int ll_cap = 0;
     double *Zcube = nullptr;
@@ -209,7 +216,7 @@ struct signer_chain {
         cudaSetDevice(device);
         if (own_stream) cudaStreamSynchronize(own_stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
-        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, col, ll_ring, Zcube, stats}) cudaFree(p);
+        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats}) cudaFree(p);
         for (int b = 0; b < 2; ++b) {
             cudaFree(Zin[b]); cudaFree(Znj[b]);
             free_ring(ring[b]);
@@ -263,6 +270,7 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     const int tgt = c->zcur ^ 1;
     ZParams p{};
     p.I = c->I; p.J = c->J; p.K = c->K;
+    p.col0 = c->col0; p.Jglobal = c->data->Jglobal;
     p.cell_row = c->data->cell_row; p.cell_col = c->data->cell_col; p.cell_n = c->data->cell_n;
     p.n_cells = c->data->n_cells; p.n_batches = c->n_batches;
     p.P = c->P; p.E = c->E;
@@ -289,7 +297,9 @@ int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double
 {
     PParams p{};
     p.IK = (int)c->nP; p.P = c->P; p.Ap = c->Ap; p.Bp = c->Bp;
-    p.Zin = c->Zin[c->zcur]; p.corrE_part = c->corrE_part; p.n_seg = c->n_seg; p.n_shards = 1;
+    p.Zin = c->Zin[c->zcur];
+    if (c->n_shards > 1) { p.corrE_part = c->corrE_all; p.n_seg = c->n_shards; p.n_shards = c->n_shards; }
+    else { p.corrE_part = c->corrE_part; p.n_seg = c->n_seg; p.n_shards = 1; }
     p.Ps_slot = Ps; p.Aps_slot = Aps; p.Bps_slot = Bps;
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
     {
@@ -305,6 +315,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
 {
     EParams p{};
     p.I = c->I; p.J = c->J; p.Jp = c->Jp; p.K = c->K;
+    p.col0 = c->col0;
     p.W = c->data->W; p.P = c->P; p.E = c->E; p.Ae = c->Ae; p.Be = c->Be;
     p.Znj = c->Znj[c->zcur]; p.corrE_part = c->corrE_part;
     p.do_corrE = do_corrE;
@@ -319,16 +330,22 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     return SIGNER_OK;
 }
 
+int launch_loglik_cols(signer_chain *c)
+{
+    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col + c->col0, 0};
+    const size_t smem = sizeof(double) * (size_t)(c->K * 33 + kLLChunk * c->K + kLLChunk * 33);
+    loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SIGNER_OK;
+}
+
 int launch_loglik(signer_chain *c, double *out)
 {
-    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col, 0};
-    const size_t smem = sizeof(double) * (size_t)(c->K * 33 + kLLChunk * c->K + kLLChunk * 33);
-    {
-        ProfScope ps(c, 3);
-        loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
-        tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out);
-    }
-    c->launches += 2;
+    ProfScope ps(c, 3);
+    ST(launch_loglik_cols(c));
+    tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out);
+    c->launches++;
     CU(cudaGetLastError());
     return SIGNER_OK;
 }
@@ -347,29 +364,45 @@ void prefault(double *p, size_t n_doubles)
 struct Slots { double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr; };
 
 // One sweep: the seven steps of `order` (0 = skip) regrouped into at most three launches.
-int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slots *slots, double *zcube)
-{
+struct SweepPlan {
     Ops pops{0, 0u}, eops{0, 0u};
+    bool has3 = false;
+    struct Item { int pos, kind; } items[3];
+    int n = 0;
+};
+
+SweepPlan plan_sweep(const int order[7], bool Pfixed)
+{
+    SweepPlan pl;
     int pos1 = -1, posP = -1, posE = -1;
-    bool has2 = false, has3 = false;
+    bool has2 = false;
     for (int f = 0; f < 7; ++f) {
         const int s = order[f];
         if (s == 1) { if (pos1 < 0) pos1 = f; }
         else if (s == 2 || s == 4 || s == 6) {
-            if (c->Pfixed) continue;                    // guards of src/gibbs_2.cpp:311,313,315
-            if (pops.n < 3) pops.push(s);
+            if (Pfixed) continue;                       // guards of src/gibbs_2.cpp:311,313,315
+            if (pl.pops.n < 3) pl.pops.push(s);
             if (s == 2) { posP = f; has2 = true; } else if (!has2 && posP < 0) posP = f;
         } else if (s == 3 || s == 5 || s == 7) {
-            if (eops.n < 3) eops.push(s);
-            if (s == 3) { posE = f; has3 = true; } else if (!has3 && posE < 0) posE = f;
+            if (pl.eops.n < 3) pl.eops.push(s);
+            if (s == 3) { posE = f; pl.has3 = true; } else if (!pl.has3 && posE < 0) posE = f;
         }
     }
-    struct Item { int pos, kind; } items[3];
-    int n = 0;
-    if (pos1 >= 0) items[n++] = {pos1, 1};
-    if (pops.n) items[n++] = {posP, 2};
-    if (eops.n) items[n++] = {posE, 3};
-    std::sort(items, items + n, [](const Item &a, const Item &b) { return a.pos < b.pos; });
+    if (pos1 >= 0) pl.items[pl.n++] = {pos1, 1};
+    if (pl.pops.n) pl.items[pl.n++] = {posP, 2};
+    if (pl.eops.n) pl.items[pl.n++] = {posE, 3};
+    for (int a = 1; a < pl.n; ++a)                      // at most three items: insertion sort by position
+        for (int b = a; b > 0 && pl.items[b].pos < pl.items[b - 1].pos; --b) std::swap(pl.items[b], pl.items[b - 1]);
+    return pl;
+}
+
+int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slots *slots, double *zcube)
+{
+    const SweepPlan pl = plan_sweep(order, c->Pfixed != 0);
+    const Ops &pops = pl.pops, &eops = pl.eops;
+    const bool has3 = pl.has3;
+    const SweepPlan::Item *items = pl.items;
+    const int n = pl.n;
     bool storedP = false, storedE = false;
     for (int t = 0; t < n; ++t) {
         if (items[t].kind == 1) ST(launch_z(c, sweep, kStZ, zcube));
@@ -452,7 +485,8 @@ int fetch_state(signer_chain *c, signer_outputs *out)
     return SIGNER_OK;
 }
 
-int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st, const signer_opts *o, signer_chain **out)
+int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st, const signer_opts *o, signer_chain **out,
+                 bool deferred_init = false)
 {
     if (!st || !o || !out) return fail(SIGNER_ERR_ARG, "null argument");
     if (o->Zfixed || o->Thetafixed || o->Afixed)
@@ -507,6 +541,11 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->ksplit = (K + kEGroup - 1) / kEGroup;
 
     // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device
+    if (deferred_init) {                                  // a column shard: its peers take part (sharded_run)
+        CU(cudaStreamSynchronize(c->stream));
+        *out = c.release();
+        return SIGNER_OK;
+    }
     if (st->Z) {
         double *slab[2] = {nullptr, nullptr};
         const size_t ns = (size_t)c->I * c->J;
@@ -615,6 +654,324 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         }
     }
     if (out) ST(fetch_state(c, out));
+    return SIGNER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Genome-column sharding: one chain over several GPUs.  Shard g owns the 128-genome
+// segments [g*n_seg/N, (g+1)*n_seg/N) -- M, W, E, Ae, Be, Znj for those genomes; P, Ap, Bp are
+// replicated and updated redundantly with identical Philox counters, so they stay identical.
+// Per sweep two exchanges of I*K values: the integer sums Zin after step 1 and the shards' ordered
+// W E' sums after step 3 (every shard fills only its slot of an [N][I*K] buffer, so the all-reduce
+// adds zeros and is exact in any order); per evaluation sweep one all-reduce of the per-genome
+// log-likelihood terms.  Results are bit-identical to the oracle run with nshards = N.
+// NCCL (all-reduce over NVLink) is loaded lazily; shards placed on ONE device are emulated with a
+// summing kernel so that the logic is testable on a single GPU.
+// ------------------------------------------------------------------------------------------------
+typedef void *nccl_comm_t;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+    }
+};
+constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0;   // nccl.h: ncclInt32, ncclFloat64, ncclSum
+
+struct ShardSet {
+    int n = 0;
+    bool same_device = true;
+    std::vector<signer_chain *> sh;
+    std::vector<nccl_comm_t> comms;
+    NcclApi nccl;
+    void **ptr_tab = nullptr;        // device table of buffer pointers for the same-device emulation
+    ~ShardSet()
+    {
+        for (auto *c : sh) delete c;
+        for (auto cm : comms) if (cm && nccl.CommDestroy) nccl.CommDestroy(cm);
+        if (ptr_tab) cudaFree(ptr_tab);
+    }
+};
+
+// all-reduce (sum) of one buffer per shard, in place
+template <typename T>
+int shard_allreduce(ShardSet &S, const std::vector<T *> &bufs, size_t count)
+{
+    if (S.n == 1) return SIGNER_OK;
+    if (S.same_device) {
+        signer_chain *c0 = S.sh[0];
+        CU(cudaSetDevice(c0->device));
+        CU(cudaMemcpyAsync(S.ptr_tab, bufs.data(), sizeof(void *) * S.n, cudaMemcpyHostToDevice, c0->stream));
+        sum_shards<T><<<(unsigned)std::min<size_t>((count + 255) / 256, 1024), 256, 0, c0->stream>>>(reinterpret_cast<T *const *>(S.ptr_tab), S.n, count);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c0->stream));    // the host-side pointer table is reused by the next call
+        return SIGNER_OK;
+    }
+    const int dt = sizeof(T) == 4 ? kNcclInt32 : kNcclFloat64;
+    int rc = S.nccl.GroupStart();
+    for (int g = 0; g < S.n && rc == 0; ++g)
+        rc = S.nccl.AllReduce(bufs[g], bufs[g], count, dt, kNcclSum, S.comms[g], S.sh[g]->stream);
+    const int rc2 = S.nccl.GroupEnd();
+    if (rc || rc2) return fail(SIGNER_ERR_NCCL, std::string("ncclAllReduce: ") + (S.nccl.GetErrorString ? S.nccl.GetErrorString(rc ? rc : rc2) : "error"));
+    return SIGNER_OK;
+}
+
+int shard_launch_z(ShardSet &S, uint32_t sweep, uint32_t stream_id, bool cube)
+{
+    std::vector<int *> zin(S.n);
+    for (int g = 0; g < S.n; ++g) {
+        signer_chain *c = S.sh[g];
+        CU(cudaSetDevice(c->device));
+        ST(launch_z(c, sweep, stream_id, cube ? c->Zcube : nullptr));
+        zin[g] = c->Zin[c->zcur];
+    }
+    return shard_allreduce<int>(S, zin, S.sh[0]->nP);
+}
+
+int shard_launch_e(ShardSet &S, uint32_t sweep, const Ops &ops, int do_corrE, const std::vector<Slots> *slots)
+{
+    std::vector<double *> all(S.n);
+    for (int g = 0; g < S.n; ++g) {
+        signer_chain *c = S.sh[g];
+        CU(cudaSetDevice(c->device));
+        const Slots *sl = slots ? &(*slots)[g] : nullptr;
+        ST(launch_e(c, sweep, ops, do_corrE, sl ? sl->Es : nullptr, sl ? sl->Aes : nullptr, sl ? sl->Bes : nullptr));
+        if (do_corrE) {
+            CU(cudaMemsetAsync(c->corrE_all, 0, sizeof(double) * c->nP * S.n, c->stream));
+            seg_reduce<<<((int)c->nP + 127) / 128, 128, 0, c->stream>>>(c->corrE_part, c->n_seg, (int)c->nP, c->corrE_all + c->nP * g);
+            CU(cudaGetLastError());
+        }
+        all[g] = c->corrE_all;
+    }
+    if (do_corrE) return shard_allreduce<double>(S, all, S.sh[0]->nP * S.n);
+    return SIGNER_OK;
+}
+
+// column terms of every shard into its part of the global array, all-reduce, tree on every shard
+int shard_loglik(ShardSet &S, int mode_lgm, double *out0)
+{
+    std::vector<double *> cols(S.n);
+    for (int g = 0; g < S.n; ++g) {
+        signer_chain *c = S.sh[g];
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)c->data->n2, c->stream));
+        if (mode_lgm) {
+            LLParams lp{c->I, c->J, c->Jp, 1, c->data->Mrow, c->data->W, nullptr, nullptr, c->col + c->col0, 1};
+            const size_t smem = sizeof(double) * (size_t)(1 * 33 + kLLChunk * 1 + kLLChunk * 33);
+            loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
+            CU(cudaGetLastError());
+        } else {
+            ST(launch_loglik_cols(c));
+        }
+        cols[g] = c->col;
+    }
+    ST(shard_allreduce<double>(S, cols, (size_t)S.sh[0]->data->n2));
+    for (int g = 0; g < S.n; ++g) {
+        signer_chain *c = S.sh[g];
+        CU(cudaSetDevice(c->device));
+        if (mode_lgm) tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, nullptr, c->data->lgm);
+        else if (g == 0) tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out0);
+        CU(cudaGetLastError());
+    }
+    return SIGNER_OK;
+}
+
+int shard_sync(ShardSet &S)
+{
+    for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); }
+    return SIGNER_OK;
+}
+
+int sharded_run(const signer_problem *pr, const signer_state *st, const signer_opts *o, signer_outputs *out,
+                const int32_t *devices, int n_dev)
+{
+    const int I = pr->I, J = pr->J, K = pr->K;
+    if (n_dev < 1 || n_dev > 64) return fail(SIGNER_ERR_ARG, "sharded run: 1..64 shards");
+    const int n_seg = (J + kSeg - 1) / kSeg;
+    if (n_dev > n_seg) return fail(SIGNER_ERR_ARG, "sharded run: more shards than 128-genome segments");
+    ShardSet S;
+    S.n = n_dev;
+    for (int g = 1; g < n_dev; ++g) if (devices[g] != devices[0]) S.same_device = false;
+    if (!S.same_device) {
+        for (int a = 0; a < n_dev; ++a) for (int b = a + 1; b < n_dev; ++b)
+            if (devices[a] == devices[b]) return fail(SIGNER_ERR_ARG, "sharded run: devices must be all distinct or all the same");
+        if (!S.nccl.load()) return fail(SIGNER_ERR_NCCL, "cannot load libnccl.so.2");
+        S.comms.assign(n_dev, nullptr);
+        std::vector<int> devs(devices, devices + n_dev);
+        const int rc = S.nccl.CommInitAll(S.comms.data(), n_dev, devs.data());
+        if (rc) return fail(SIGNER_ERR_NCCL, std::string("ncclCommInitAll: ") + (S.nccl.GetErrorString ? S.nccl.GetErrorString(rc) : "error"));
+    }
+    // create the shards
+    for (int g = 0; g < n_dev; ++g) {
+        const int s0 = (int)((long long)g * n_seg / n_dev), s1 = (int)((long long)(g + 1) * n_seg / n_dev);
+        const int c0 = s0 * kSeg, c1 = std::min(J, s1 * kSeg), Jg = c1 - c0;
+        std::shared_ptr<DeviceData> d;
+        ST(upload_data(devices[g], I, Jg, pr->M + (size_t)I * c0, pr->W + (size_t)I * c0, d, c0, J));
+        signer_state sg = *st;
+        sg.Z = nullptr;                                  // the cube (if any) is reduced below, per shard
+        sg.E = st->E + (size_t)K * c0; sg.Ae = st->Ae + (size_t)K * c0; sg.Be = st->Be + (size_t)K * c0;
+        signer_chain *c = nullptr;
+        signer_opts og = *o;
+        og.device = devices[g];
+        ST(chain_create(d, K, &sg, &og, &c, /*deferred_init=*/true));
+        S.sh.push_back(c);
+        c->shard = g; c->n_shards = n_dev; c->col0 = c0;
+        CU(cudaMalloc(&c->corrE_all, sizeof(double) * c->nP * n_dev));
+        if (S.same_device && g > 0) { CU(cudaStreamSynchronize(c->stream)); c->stream = S.sh[0]->stream; }   // one stream: plain ordering
+    }
+    if (S.same_device) { CU(cudaSetDevice(devices[0])); CU(cudaMalloc(&S.ptr_tab, sizeof(void *) * n_dev)); }
+    ST(shard_sync(S));
+    ST(shard_loglik(S, 1, nullptr));                     // sum lgamma(M+1) over the whole cohort, on every shard
+    // initial sufficient statistics and W E'
+    if (st->Z) {
+        for (int g = 0; g < n_dev; ++g) {
+            signer_chain *c = S.sh[g];
+            CU(cudaSetDevice(c->device));
+            double *slab = nullptr;
+            const size_t ns = (size_t)I * c->J;
+            CU(cudaMalloc(&slab, ns * sizeof(double)));
+            for (int k = 0; k < K; ++k) {
+                CU(cudaMemcpyAsync(slab, st->Z + (size_t)I * J * k + (size_t)I * c->col0, ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                zslab_reduce<<<(c->J + 127) / 128, 128, 0, c->stream>>>(slab, I, c->J, K, k, c->Zin[0], c->Znj[0]);
+            }
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaFree(slab));
+            c->zcur = 0;
+        }
+        std::vector<int *> zin(n_dev);
+        for (int g = 0; g < n_dev; ++g) zin[g] = S.sh[g]->Zin[0];
+        ST(shard_allreduce<int>(S, zin, S.sh[0]->nP));
+    } else {
+        ST(shard_launch_z(S, o->sweep0, kStZinit, false));
+    }
+    if (!o->Pfixed) { Ops none{0, 0u}; ST(shard_launch_e(S, o->sweep0, none, 1, nullptr)); }
+
+    const int burn = o->burn, eval = o->eval, keep_par = o->keep_par ? 1 : 0, total = burn + eval;
+    if (burn < 0 || eval < 0) return fail(SIGNER_ERR_ARG, "burn and eval must be non-negative");
+    int cap = 1;
+    if (eval > 0) {
+        for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); ST(ensure_rings(c, eval, keep_par)); cap = c->ring_cap; }
+        for (auto *c : S.sh) cap = std::min(cap, c->ring_cap);
+        signer_chain *c0 = S.sh[0];
+        CU(cudaSetDevice(c0->device));
+        CU(cudaMalloc(&c0->ll_ring, sizeof(double) * (size_t)eval)); c0->ll_cap = eval;
+    }
+    const bool want_cube = keep_par && out->Zs && eval > 0;
+    if (want_cube) for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); CU(cudaMalloc(&c->Zcube, sizeof(double) * (size_t)I * c->J * K)); }
+
+    auto flush = [&](int r0, int cnt) -> int {            // ring slots 0..cnt-1 hold eval sweeps r0..r0+cnt-1
+        ST(shard_sync(S));
+        signer_chain *c0 = S.sh[0];
+        CU(cudaSetDevice(c0->device));
+        auto cpP = [&](double *dst, const double *src) -> int {
+            if (dst && src) CU(cudaMemcpy(dst + c0->nP * (size_t)r0, src, sizeof(double) * c0->nP * (size_t)cnt, cudaMemcpyDeviceToHost));
+            return SIGNER_OK;
+        };
+        ST(cpP(out->Ps, c0->ring[0].Ps)); ST(cpP(out->Bps, c0->ring[0].Bps)); if (keep_par) ST(cpP(out->Aps, c0->ring[0].Aps));
+        for (auto *c : S.sh) {
+            CU(cudaSetDevice(c->device));
+            auto cpE = [&](double *dst, const double *src) -> int {   // a shard's genomes are a contiguous block of every slice
+                if (dst && src)
+                    CU(cudaMemcpy2D(dst + (size_t)K * J * (size_t)r0 + (size_t)K * c->col0, sizeof(double) * (size_t)K * J, src,
+                                    sizeof(double) * c->nE, sizeof(double) * c->nE, (size_t)cnt, cudaMemcpyDeviceToHost));
+                return SIGNER_OK;
+            };
+            ST(cpE(out->Es, c->ring[0].Es)); ST(cpE(out->Bes, c->ring[0].Bes)); if (keep_par) ST(cpE(out->Aes, c->ring[0].Aes));
+        }
+        return SIGNER_OK;
+    };
+
+    int r0 = 0;
+    for (int k = 0; k < total; ++k) {
+        const uint32_t sweep = o->sweep0 + (uint32_t)k;
+        int order[7];
+        if (o->forced_order) for (int f = 0; f < 7; ++f) order[f] = o->forced_order[(size_t)7 * k + f];
+        else host_perm(o->seed, sweep, order);
+        const SweepPlan pl = plan_sweep(order, o->Pfixed != 0);
+        const bool storing = k >= burn, last = (k == total - 1);
+        const int r = k - burn, slot = storing ? r % cap : 0;
+        std::vector<Slots> slots(S.n);
+        if (storing)
+            for (int g = 0; g < S.n; ++g) {
+                signer_chain *c = S.sh[g]; Ring &rg = c->ring[0];
+                Slots &s = slots[g];
+                s.Es = rg.Es + c->nE * slot; s.Bes = rg.Bes + c->nE * slot; if (keep_par) s.Aes = rg.Aes + c->nE * slot;
+                if (g == 0) { s.Ps = rg.Ps + c->nP * slot; s.Bps = rg.Bps + c->nP * slot; if (keep_par) s.Aps = rg.Aps + c->nP * slot; }
+            }
+        bool storedP = false, storedE = false;
+        for (int t = 0; t < pl.n; ++t) {
+            if (pl.items[t].kind == 1) ST(shard_launch_z(S, sweep, kStZ, want_cube && last));
+            else if (pl.items[t].kind == 2) {
+                for (int g = 0; g < S.n; ++g) {
+                    signer_chain *c = S.sh[g];
+                    CU(cudaSetDevice(c->device));
+                    const Slots *sl = storing ? &slots[g] : nullptr;
+                    ST(launch_p(c, sweep, pl.pops, sl ? sl->Ps : nullptr, sl ? sl->Aps : nullptr, sl ? sl->Bps : nullptr));
+                }
+                storedP = true;
+            } else {
+                ST(shard_launch_e(S, sweep, pl.eops, (pl.has3 && !o->Pfixed) ? 1 : 0, storing ? &slots : nullptr));
+                storedE = true;
+            }
+        }
+        if (storing) {
+            for (int g = 0; g < S.n; ++g) {
+                signer_chain *c = S.sh[g]; const Slots &s = slots[g];
+                CU(cudaSetDevice(c->device));
+                if (!storedP && g == 0) {
+                    CU(cudaMemcpyAsync(s.Ps, c->P, c->nP * 8, cudaMemcpyDeviceToDevice, c->stream));
+                    CU(cudaMemcpyAsync(s.Bps, c->Bp, c->nP * 8, cudaMemcpyDeviceToDevice, c->stream));
+                    if (s.Aps) CU(cudaMemcpyAsync(s.Aps, c->Ap, c->nP * 8, cudaMemcpyDeviceToDevice, c->stream));
+                }
+                if (!storedE) {
+                    CU(cudaMemcpyAsync(s.Es, c->E, c->nE * 8, cudaMemcpyDeviceToDevice, c->stream));
+                    CU(cudaMemcpyAsync(s.Bes, c->Be, c->nE * 8, cudaMemcpyDeviceToDevice, c->stream));
+                    if (s.Aes) CU(cudaMemcpyAsync(s.Aes, c->Ae, c->nE * 8, cudaMemcpyDeviceToDevice, c->stream));
+                }
+            }
+            ST(shard_loglik(S, 0, S.sh[0]->ll_ring + r));
+            if (slot == cap - 1 || last) { ST(flush(r0, slot + 1)); r0 += slot + 1; }
+        }
+    }
+    ST(shard_sync(S));
+    signer_chain *c0 = S.sh[0];
+    CU(cudaSetDevice(c0->device));
+    if (eval > 0 && (out->loglik || out->bic)) {
+        std::vector<double> ll((size_t)eval);
+        CU(cudaMemcpy(ll.data(), c0->ll_ring, sizeof(double) * (size_t)eval, cudaMemcpyDeviceToHost));
+        const double pen = (double)K * (double)(I + J) * std::log((double)J);
+        for (int r = 0; r < eval; ++r) { if (out->loglik) out->loglik[r] = ll[r]; if (out->bic) out->bic[r] = 2.0 * ll[r] - pen; }
+    }
+    auto cp = [&](void *dst, const void *src, size_t bytes) -> int { if (dst) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return SIGNER_OK; };
+    ST(cp(out->P, c0->P, c0->nP * 8)); ST(cp(out->Ap, c0->Ap, c0->nP * 8)); ST(cp(out->Bp, c0->Bp, c0->nP * 8));
+    ST(cp(out->Zin, c0->Zin[c0->zcur], c0->nP * 4));
+    for (auto *c : S.sh) {
+        CU(cudaSetDevice(c->device));
+        const size_t off = (size_t)K * c->col0;
+        ST(cp(out->E ? out->E + off : nullptr, c->E, c->nE * 8)); ST(cp(out->Ae ? out->Ae + off : nullptr, c->Ae, c->nE * 8));
+        ST(cp(out->Be ? out->Be + off : nullptr, c->Be, c->nE * 8)); ST(cp(out->Znj ? out->Znj + off : nullptr, c->Znj[c->zcur], c->nE * 4));
+        if (want_cube)
+            for (int k = 0; k < K; ++k)
+                CU(cudaMemcpy(out->Zs + (size_t)I * J * k + (size_t)I * c->col0, c->Zcube + (size_t)I * c->J * k, sizeof(double) * (size_t)I * c->J,
+                              cudaMemcpyDeviceToHost));
+    }
     return SIGNER_OK;
 }
 
@@ -798,6 +1155,16 @@ int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W, s
     for (int d = 0; d < n_devices; ++d)
         if (rcs[d] != SIGNER_OK) return fail(rcs[d], errs[d]);
     return SIGNER_OK;
+}
+
+int signer_gibbs_run_sharded(const signer_problem *pr, const signer_state *st, const signer_opts *o, signer_outputs *out,
+                             const int32_t *devices, int32_t n_devices)
+{
+    g_err.clear();
+    if (!pr || !st || !o || !out || !devices) return fail(SIGNER_ERR_ARG, "null argument");
+    if (o->Zfixed || o->Thetafixed || o->Afixed)
+        return fail(SIGNER_ERR_UNSUPPORTED, "Zfixed/Thetafixed/Afixed=TRUE are not reachable from signeR and not implemented");
+    return sharded_run(pr, st, o, out, devices, n_devices);
 }
 
 // ---- test hooks

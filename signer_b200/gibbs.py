@@ -113,7 +113,7 @@ class _Buffers:
 
 def GibbsSamplerCpp(M, W, Z, P, E, Ap, Bp, Ae, Be, ap, bp, ae, be, lp, le, var_ap, var_ae, burn, eval,
                     Pfixed, Zfixed, Thetafixed, Afixed, keep_par, *, seed=None, sweep0=0, device=0,
-                    forced_order=None):
+                    forced_order=None, shard_devices=None):
     """Drop-in for the reference's GibbsSamplerCpp (src/gibbs_2.cpp:253-424).
 
     Inputs are not modified (the reference takes them by value, src/RcppExports.cpp:35-58).
@@ -141,7 +141,11 @@ def GibbsSamplerCpp(M, W, Z, P, E, Ap, Bp, Ae, Be, ap, bp, ae, be, lp, le, var_a
                     keep_par, seed, sweep0, device, forced)
     buf = _Buffers(I, J, K, eval, bool(keep_par))
     out = buf.struct()
-    check(_lib.lib().signer_gibbs_run(C.byref(pr), C.byref(st), C.byref(op), C.byref(out)))
+    if shard_devices is not None:           # one chain over several GPUs, genome columns sharded (include/signer_gibbs.h)
+        dev = np.ascontiguousarray(np.asarray(shard_devices, dtype=np.int32))
+        check(_lib.lib().signer_gibbs_run_sharded(C.byref(pr), C.byref(st), C.byref(op), C.byref(out), dev.ctypes.data_as(ip), dev.size))
+    else:
+        check(_lib.lib().signer_gibbs_run(C.byref(pr), C.byref(st), C.byref(op), C.byref(out)))
     return buf.as_list(bool(keep_par), seed)
 
 
