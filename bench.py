@@ -220,6 +220,32 @@ def run_nsig(args):
         torch.distributed.destroy_process_group()
 
 
+def run_sharded(args):
+    """Secondary metric: ONE chain with its genome columns sharded over N GPUs (BASELINE.json config 4: 1536 x 20,000,
+    K = 30), driven by one process through signer_gibbs_run_sharded (NCCL all-reduce of the I x K statistics each sweep).
+    Times the whole reference-shaped call (upload, burn-in sweeps, final state back), so the value is an end-to-end one."""
+    import signer_b200 as sg
+    from signer_b200 import synth
+    wl = args.workload if args.workload != "cfg3_96x10000_K20" else "cfg4_1536x20000_K30"
+    K = WORKLOADS[wl]["K"]
+    M, W, _, _ = synth.named(wl)
+    I, J = M.shape
+    st = synth.init_state(I, J, K, seed=4)
+    h = synth.hyper_tuple()
+    devs = list(range(args.gpus))
+    a = (st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *h)
+    from signer_b200 import _lib
+    sg.GibbsSamplerCpp(M, W, None, *a, 2, 0, False, False, False, False, False, seed=1, shard_devices=devs)     # warm-up
+    t0 = time.perf_counter()
+    r = sg.GibbsSamplerCpp(M, W, None, *a, args.steps, 0, False, False, False, False, False, seed=1, shard_devices=devs)
+    dt = time.perf_counter() - t0
+    loop_ms = float(_lib.lib().signer_last_loop_ms())          # the library's own clock around the sweep loop
+    print(json.dumps(dict(metric="sharded_gibbs_sweeps_per_s", value=args.steps / (loop_ms * 1e-3), unit="sweeps/s", n_gpus=args.gpus,
+                          steps=args.steps, ms_per_step=loop_ms / args.steps, higher_is_better=True, scaling="strong",
+                          config=dict(workload=wl, I=I, J=J, K=K, shards=args.gpus, collective="ncclAllReduce of Zin (int32) and W E' sums (f64), 2*I*K values per sweep"),
+                          call_seconds=dt, upload_and_setup_seconds=dt - loop_ms * 1e-3, zin_total=int(r.Zin.sum()), m_total=int(M.sum()))), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,7 +255,7 @@ def main():
     ap.add_argument("--workload", default="cfg3_96x10000_K20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="sweeps", choices=["sweeps", "nsig"],
+    ap.add_argument("--mode", default="sweeps", choices=["sweeps", "nsig", "sharded"],
                     help="nsig: wall time of a full nsig model-selection sweep (secondary metric of BASELINE.json)")
     ap.add_argument("--nsig-range", default="2,10")
     ap.add_argument("--chains", type=int, default=1)
@@ -245,6 +271,9 @@ def main():
         return
     if args.mode == "nsig":
         run_nsig(args)
+        return
+    if args.mode == "sharded":
+        run_sharded(args)
         return
 
     import torch

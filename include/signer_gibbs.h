@@ -164,6 +164,9 @@ void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 
 /* Thread-local text of the last error on this thread ("" if none). */
 const char *signer_last_error(void);
+/* Wall time (ms) of the sweep loop of the last signer_gibbs_run / signer_gibbs_run_sharded on this thread: from the
+ * first sweep's launch to the last result on the host, excluding upload and set-up. */
+double signer_last_loop_ms(void);
 int signer_version(void);
 /* Number of CUDA devices visible, or a negative status. */
 int signer_device_count(void);

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <dlfcn.h>
 #include <functional>
@@ -25,6 +26,7 @@ using namespace sg;
 namespace {
 
 thread_local std::string g_err;
+thread_local double g_loop_ms = 0.0;      // wall time of the last sweep loop on this thread (sharded / stateless runs)
 
 int fail(int code, const std::string &msg)
 {
@@ -898,6 +900,8 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         return SIGNER_OK;
     };
 
+    ST(shard_sync(S));
+    const auto t_loop = std::chrono::steady_clock::now();
     int r0 = 0;
     for (int k = 0; k < total; ++k) {
         const uint32_t sweep = o->sweep0 + (uint32_t)k;
@@ -951,6 +955,7 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         }
     }
     ST(shard_sync(S));
+    g_loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
     signer_chain *c0 = S.sh[0];
     CU(cudaSetDevice(c0->device));
     if (eval > 0 && (out->loglik || out->bic)) {
@@ -981,6 +986,7 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
 extern "C" {
 
 const char *signer_last_error(void) { return g_err.c_str(); }
+double signer_last_loop_ms(void) { return g_loop_ms; }
 int signer_version(void) { return SIGNER_ABI_VERSION; }
 
 int signer_device_count(void)
@@ -1088,7 +1094,9 @@ int signer_gibbs_run(const signer_problem *pr, const signer_state *st, const sig
     if (!pr || !st || !o || !out) return fail(SIGNER_ERR_ARG, "null argument");
     signer_chain *c = nullptr;
     ST(signer_chain_create(pr, st, o, &c));
+    const auto t_loop = std::chrono::steady_clock::now();
     const int rc = chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, out);
+    g_loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
     const std::string keep = g_err;
     signer_chain_destroy(c);
     g_err = keep;
