@@ -161,6 +161,8 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
 
 // z_alloc_fused may need more than 48 KB of dynamic shared memory; raise the limit once per device to the
 // architectural maximum so that concurrent chains with different K never race on the attribute.
+int g_z_dyn_smem_max[64] = {0};
+
 int ensure_device_setup(int device)
 {
     static std::mutex mu;
@@ -169,7 +171,12 @@ int ensure_device_setup(int device)
     if (device < 0 || device >= 64) return fail(SIGNER_ERR_ARG, "device ordinal out of range");
     if (done[device]) return SIGNER_OK;
     CU(cudaSetDevice(device));
-    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    int optin = 0;
+    CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, z_alloc_fused));
+    g_z_dyn_smem_max[device] = optin - (int)fa.sharedSizeBytes;
+    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
     done[device] = true;
     return SIGNER_OK;
 }
@@ -533,8 +540,8 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->z_warp_smem = (int)z_smem_bytes_per_warp(K);
     c->z_zin_smem = (c->nP * sizeof(int) <= (size_t)kZinSmemMax) ? 1 : 0;
     const size_t zsm = (size_t)c->z_warp_smem * kZWarps + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
-    if (zsm > (size_t)226 * 1024) return fail(SIGNER_ERR_ARG, "z_alloc_fused: K too large for shared memory");
     ST(ensure_device_setup(c->device));
+    if (zsm > (size_t)g_z_dyn_smem_max[c->device]) return fail(SIGNER_ERR_ARG, "z_alloc_fused: K too large for shared memory");
     int occ = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * kZWarps, zsm));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
