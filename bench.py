@@ -196,7 +196,7 @@ def run_nsig(args):
     from signer_b200 import dist, synth
     from signer_b200.signer import batch_bics
     rank, world, local = dist.init()
-    wl = args.workload if args.workload != "cfg3_96x10000_K20" else "cfg2_96x560"
+    wl = args.workload
     M, W, _, _ = synth.named(wl)
     I, J = M.shape
     lo, hi = (int(x) for x in args.nsig_range.split(","))
@@ -235,7 +235,7 @@ def run_sharded(args):
     Times the whole reference-shaped call (upload, burn-in sweeps, final state back), so the value is an end-to-end one."""
     import signer_b200 as sg
     from signer_b200 import synth
-    wl = args.workload if args.workload != "cfg3_96x10000_K20" else "cfg4_1536x20000_K30"
+    wl = args.workload
     K = WORKLOADS[wl]["K"]
     M, W, _, _ = synth.named(wl)
     I, J = M.shape
@@ -261,7 +261,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3_96x10000_K20", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: cfg3_96x10000_K20 (sweeps), cfg2_96x560 (nsig), cfg4_1536x20000_K30 (sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mode", default="sweeps", choices=["sweeps", "nsig", "sharded"],
@@ -270,6 +271,8 @@ def main():
     ap.add_argument("--chains", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload is None:
+        args.workload = {"sweeps": "cfg3_96x10000_K20", "nsig": "cfg2_96x560", "sharded": "cfg4_1536x20000_K30"}[args.mode]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
