@@ -187,3 +187,16 @@ def test_cuda_equals_reference_source(sg, oracle):
     for slot, k in ((2, "Ps"), (3, "Es"), (4, "Aps"), (5, "Bps"), (6, "Aes"), (7, "Bes")):
         assert_bits_equal(got[slot], ref[k], k)
     assert_bits_equal(got[0][:, :, :, 0], ref["Z"], "Zs")
+
+
+@pytest.mark.parametrize("I,J,K,note", [
+    (40, 70, 33, "K odd and > 32: scalar E loads, no touched-class mask"),
+    (300, 60, 40, "I*K*4 = 48 KB > 40 KB: Zin accumulated with global atomics, not in shared memory"),
+    (1536, 40, 30, "pentanucleotide contexts (config 4 rows)"),
+    (96, 300, 64, "K = 64"),
+])
+def test_large_k_and_wide_context_paths(sg, oracle, I, J, K, note):
+    M, W, st = small_problem(I=I, J=J, K=K, seed=K, burden=20.0 * I)
+    M[0, 0] = 900.0; M[1, 1] = 40000.0
+    got, want = run_both(sg, oracle, M, W, st, K, burn=4, eval=2, keep_par=True, seed=K * 7)
+    compare_all(got, want)
