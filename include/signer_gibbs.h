@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIGNER_ABI_VERSION 1
+#define SIGNER_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -82,6 +82,12 @@ typedef struct {
     double *bic;                 /* R: 2*loglik - K*(I+J)*log(J)        (R/cpp_eBayesNMF.R:186) */
     double *P, *E, *Ap, *Bp, *Ae, *Be;   /* final state (what R re-reads from the last slice, :108-139) */
     int32_t *Zin, *Znj;          /* final sufficient statistics sum_j Z (I x K), sum_i Z (K x J) */
+    double *Phat, *Ehat;         /* I x K, K x J: posterior medians of the NORMALISED samples, computed on the device
+                                    (replaces Normalize + Median_sign/Median_exp, R/Definition_SignExp_object.R:116-150,
+                                    :259,:297, called at R/cpp_eBayesNMF.R:187-189; signatures in sampler order, the
+                                    re-ordering by total exposure :190-198 is left to the host).  Lets a final fit return
+                                    its point estimates without copying the sample cubes; needs eval * 8 * K * (I+J)
+                                    bytes of device memory twice. */
 } signer_outputs;
 
 /* Stateless drop-in for one GibbsSamplerCpp call. */

@@ -44,7 +44,7 @@ class Outputs(C.Structure):
     _fields_ = [("Zs", dp), ("Ps", dp), ("Es", dp), ("Aps", dp), ("Aes", dp), ("Bps", dp), ("Bes", dp),
                 ("loglik", dp), ("bic", dp),
                 ("P", dp), ("E", dp), ("Ap", dp), ("Bp", dp), ("Ae", dp), ("Be", dp),
-                ("Zin", ip), ("Znj", ip)]
+                ("Zin", ip), ("Znj", ip), ("Phat", dp), ("Ehat", dp)]
 
 
 class Task(C.Structure):

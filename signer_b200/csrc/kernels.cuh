@@ -557,6 +557,99 @@ __global__ void stats_reduce(const double *a, const double *b, size_t n, double 
 }
 
 // ------------------------------------------------------------------------------------------------
+// posterior summaries on the device (R/Definition_SignExp_object.R:116-122 normalisation, :129-143 and
+// :259,:297 medians; R/cpp_eBayesNMF.R:187-189): Phat = median_r P[i,k,r]/s_k[r], Ehat = median_r E[k,j,r]*s_k[r],
+// s_k[r] = sum_i P[i,k,r].
+// ------------------------------------------------------------------------------------------------
+__global__ void sig_sums(const double *Ps, int I, int K, int R, double *s /* [R][K] */)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * K) return;
+    const int r = t / K, k = t - r * K;
+    const double *col = Ps + (size_t)r * I * K + (size_t)I * k;
+    double acc = 0.0;
+    for (int i = 0; i < I; ++i) acc = acc + col[i];
+    s[t] = acc;
+}
+
+// X [R][n] -> T [n][R], scaled by the sample's signature sum: mode 0 (signatures, element i + I*k): X / s ;
+// mode 1 (exposures, element k + K*j): X * s.  32 x 32 tiles through shared memory: coalesced both ways.
+__global__ void norm_transpose(const double *X, const double *s, int n, int R, int I, int K, int mode, double *T)
+{
+    __shared__ double tile[32][33];
+    const int e0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int e = e0 + threadIdx.x, r = r0 + rr;
+        double v = 0.0;
+        if (e < n && r < R) {
+            const int k = mode == 0 ? e / I : e % K;
+            const double sk = s[(size_t)r * K + k];
+            const double x = X[(size_t)r * n + e];
+            v = mode == 0 ? x / sk : x * sk;
+        }
+        tile[rr][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int ee = threadIdx.y; ee < 32; ee += blockDim.y) {
+        const int e = e0 + ee, r = r0 + threadIdx.x;
+        if (e < n && r < R) T[(size_t)e * R + r] = tile[threadIdx.x][ee];
+    }
+}
+
+// rank-th smallest (0-based) of R non-negative doubles by MSB-first radix selection on their bit patterns
+__device__ unsigned long long radix_select(const double *v, int R, int rank, int *hist /* [256] shared, per warp */)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long prefix = 0, mask = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (int r = lane; r < R; r += 32) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[r]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ULL)], 1);
+        }
+        __syncwarp();
+        int mine = 0;                                    // lane owns bins 8*lane .. 8*lane+7
+        for (int b = 0; b < 8; ++b) mine += hist[8 * lane + b];
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+        const int excl = incl - mine;
+        const bool here = rank >= excl && rank < incl;
+        int bucket = 0, below = 0;
+        if (here) {
+            int cum = excl;
+            for (int b = 0; b < 8; ++b) {
+                const int h = hist[8 * lane + b];
+                if (rank < cum + h) { bucket = 8 * lane + b; below = cum; break; }
+                cum += h;
+            }
+        }
+        const unsigned src = __ballot_sync(kFull, here);
+        const int from = __ffs(src) - 1;
+        bucket = __shfl_sync(kFull, bucket, from);
+        below = __shfl_sync(kFull, below, from);
+        rank -= below;
+        prefix |= (unsigned long long)bucket << shift;
+        mask |= 255ULL << shift;
+        __syncwarp();
+    }
+    return prefix;
+}
+
+// one warp per element: median over the R samples of T[e][.] (mean of the two middle values when R is even, like R's median())
+__global__ void median_rows(const double *T, int n, int R, double *out)
+{
+    __shared__ int hist[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + warp;
+    if (e >= n) return;
+    const double *v = T + (size_t)e * R;
+    const double a = __longlong_as_double((long long)radix_select(v, R, (R - 1) / 2, hist[warp]));
+    const double b = (R & 1) ? a : __longlong_as_double((long long)radix_select(v, R, R / 2, hist[warp]));
+    if (lane == 0) out[e] = (a + b) / 2.0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // column sharding: a shard adds its own W E' segment partials in order into its slot of the gathered
 // buffer (the other slots stay zero, so the all-reduce over shards is exact in any order)
 // ------------------------------------------------------------------------------------------------

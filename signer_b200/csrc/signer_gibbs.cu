@@ -203,6 +203,7 @@ struct signer_chain {
     int ll_cap = 0;
     double *Zcube = nullptr;
     double *stats = nullptr;
+    double *sumPs = nullptr, *sumEs = nullptr;   // full-length sample stores for the device-side summaries
     unsigned long long *tile_counter = nullptr;
     unsigned long long z_launches = 0;
     int z_grid = 0, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
@@ -225,7 +226,7 @@ struct signer_chain {
         cudaSetDevice(device);
         if (own_stream) cudaStreamSynchronize(own_stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
-        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats}) cudaFree(p);
+        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats, sumPs, sumEs}) cudaFree(p);
         for (int b = 0; b < 2; ++b) {
             cudaFree(Zin[b]); cudaFree(Znj[b]);
             free_ring(ring[b]);
@@ -472,10 +473,36 @@ int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signe
         CU(cudaMemcpyAsync(dst + per * (size_t)r0, src, sizeof(double) * per * (size_t)cnt, cudaMemcpyDeviceToHost, c->copy_stream));
         return SIGNER_OK;
     };
-    ST(cp(out->Ps, r.Ps, c->nP)); ST(cp(out->Es, r.Es, c->nE));
+    if (!c->sumPs) { ST(cp(out->Ps, r.Ps, c->nP)); ST(cp(out->Es, r.Es, c->nE)); }   // else: from the full-length stores at the end
     ST(cp(out->Bps, r.Bps, c->nP)); ST(cp(out->Bes, r.Bes, c->nE));
     if (keep_par) { ST(cp(out->Aps, r.Aps, c->nP)); ST(cp(out->Aes, r.Aes, c->nE)); }
     CU(cudaEventRecord(r.copied, c->copy_stream));
+    return SIGNER_OK;
+}
+
+// Phat / Ehat from the full-length sample stores (see include/signer_gibbs.h)
+int device_summaries(signer_chain *c, int R, double *Phat, double *Ehat)
+{
+    double *s = nullptr, *T = nullptr, *med = nullptr;
+    const size_t nmax = std::max(c->nP, c->nE);
+    CU(cudaMalloc(&s, sizeof(double) * (size_t)R * c->K));
+    CU(cudaMalloc(&T, sizeof(double) * nmax * (size_t)R));
+    CU(cudaMalloc(&med, sizeof(double) * nmax));
+    sig_sums<<<(R * c->K + 127) / 128, 128, 0, c->stream>>>(c->sumPs, c->I, c->K, R, s);
+    for (int mode = 0; mode < 2; ++mode) {
+        const size_t n = mode == 0 ? c->nP : c->nE;
+        double *dst = mode == 0 ? Phat : Ehat;
+        if (!dst) continue;
+        norm_transpose<<<dim3((unsigned)((n + 31) / 32), (unsigned)((R + 31) / 32)), dim3(32, 8), 0, c->stream>>>(
+            mode == 0 ? c->sumPs : c->sumEs, s, (int)n, R, c->I, c->K, mode, T);
+        median_rows<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>(T, (int)n, R, med);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dst, med, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->launches += 2;
+    }
+    c->launches += 1;
+    cudaFree(s); cudaFree(T); cudaFree(med);
     return SIGNER_OK;
 }
 
@@ -599,6 +626,12 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         if (!c->Zcube) CU(cudaMalloc(&c->Zcube, sizeof(double) * (size_t)c->I * c->J * c->K));
         zcube = c->Zcube;
     }
+    const bool summ = out && eval > 0 && (out->Phat || out->Ehat);
+    if (summ) {                                           // full-length stores for Ps and Es
+        cudaFree(c->sumPs); cudaFree(c->sumEs); c->sumPs = c->sumEs = nullptr;
+        CU(cudaMalloc(&c->sumPs, sizeof(double) * c->nP * (size_t)eval));
+        CU(cudaMalloc(&c->sumEs, sizeof(double) * c->nE * (size_t)eval));
+    }
     const int total = burn + eval, cap = std::max(1, c->ring_cap);
     int chunk_r0 = 0;
     std::vector<std::thread> faulters;
@@ -627,6 +660,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             s.Ps = rg.Ps + c->nP * slot; s.Es = rg.Es + c->nE * slot;
             s.Bps = rg.Bps + c->nP * slot; s.Bes = rg.Bes + c->nE * slot;
             if (keep_par) { s.Aps = rg.Aps + c->nP * slot; s.Aes = rg.Aes + c->nE * slot; }
+            if (summ) { s.Ps = c->sumPs + c->nP * (size_t)r; s.Es = c->sumEs + c->nE * (size_t)r; }
             const bool last = (k == total - 1);
             // Zs keeps only the latest Z (src/gibbs_2.cpp:323): store the cube in the last sweep only
             ST(enqueue_sweep(c, sweep, order, &s, last ? zcube : nullptr));
@@ -651,6 +685,12 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         if (zcube && out->Zs) {
             // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined
             CU(cudaMemcpy(out->Zs, zcube, sizeof(double) * (size_t)c->I * c->J * c->K, cudaMemcpyDeviceToHost));
+        }
+        if (summ) {
+            if (out->Ps) CU(cudaMemcpy(out->Ps, c->sumPs, sizeof(double) * c->nP * (size_t)eval, cudaMemcpyDeviceToHost));
+            if (out->Es) CU(cudaMemcpy(out->Es, c->sumEs, sizeof(double) * c->nE * (size_t)eval, cudaMemcpyDeviceToHost));
+            ST(device_summaries(c, eval, out->Phat, out->Ehat));
+            cudaFree(c->sumPs); cudaFree(c->sumEs); c->sumPs = c->sumEs = nullptr;
         }
         if (out->loglik || out->bic) {
             std::vector<double> ll((size_t)eval);

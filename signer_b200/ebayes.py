@@ -86,9 +86,11 @@ def initial_state(M, W, n, ap, bp, ae, be, lp, le, P=None, fixP=False, start="ra
 
 def eBayesNMF(M, W, n, ap, bp, ae, be, lp, le, var_ap=10, var_ae=10, P=None, fixP=False, start="random",
               burn_it=500, eval_it=1000, estimate_hyper=False, EM_lim=100, EM_eval_it=100, keep_param=False,
-              *, rng=None, device=0, verbose=False, keep_samples=True):
+              *, rng=None, device=0, verbose=False, keep_samples=True, device_summaries=False):
     """Returns the reference's list: [Phat, Ehat, Bics, SE, Aps, Bps, Aes, Bes, hyper] with the four
-    parameter cubes None unless keep_param (R's list positions [[1]]..[[9]])."""
+    parameter cubes None unless keep_param (R's list positions [[1]]..[[9]]).
+    keep_samples=False, device_summaries=True: Phat/Ehat come from the device (normalisation and medians
+    computed there) and no sample cube is copied to the host; SE is then None."""
     rng = rng if rng is not None else np.random.default_rng(gibbs.next_seed())
     M = np.asfortranarray(np.asarray(M, dtype=np.float64))
     W = np.asfortranarray(np.asarray(W, dtype=np.float64))
@@ -126,7 +128,7 @@ def eBayesNMF(M, W, n, ap, bp, ae, be, lp, le, var_ap=10, var_ae=10, P=None, fix
         if verbose:
             print("Running  Gibbs sampler for %d signature%s..." % (n, "" if n == 1 else "s"), file=sys.stderr)
         res = chain.run(burn=burn_it, eval=eval_it, keep_par=keep_param, fetch=True, want_Z=False,
-                        samples=keep_samples)                              # :165-168
+                        samples=keep_samples, summaries=(device_summaries and not keep_samples))   # :165-168
     finally:
         chain.close()
     Bics = np.array(res.bic)                                               # :180-186, computed on the device
@@ -144,6 +146,12 @@ def eBayesNMF(M, W, n, ap, bp, ae, be, lp, le, var_ap=10, var_ae=10, P=None, fix
         out[0], out[1], out[3] = Phat, Ehat, SE
         if keep_param:
             out[4], out[5], out[6], out[7] = res[4], res[5], res[6], res[7]
+    elif device_summaries:                                                 # :187-198 on the device, re-ordering here
+        Phat, Ehat = res.Phat, res.Ehat
+        if not fixP:
+            order = np.argsort(-(Ehat.sum(axis=1) * Phat.sum(axis=0)), kind="stable")
+            Phat, Ehat = np.asfortranarray(Phat[:, order]), np.asfortranarray(Ehat[order, :])
+        out[0], out[1] = Phat, Ehat
     if estimate_hyper:                                                     # :202-208
         out[8] = dict(ap=np.array(apvet), bp=np.array(bpvet), ae=np.array(aevet), be=np.array(bevet),
                       lp=np.array(lpvet), le=np.array(levet))

@@ -49,6 +49,8 @@ class SampleList(list):
     state = None
     Zin = None
     Znj = None
+    Phat = None          # device-side posterior medians of the normalised samples (when requested)
+    Ehat = None
     seed = None
 
 
@@ -74,8 +76,10 @@ def _forced(order, nsweeps):
 class _Buffers:
     """Caller-allocated outputs in the reference's shapes."""
 
-    def __init__(self, I, J, K, R, keep_par, want_Z=True, samples=True):
+    def __init__(self, I, J, K, R, keep_par, want_Z=True, samples=True, summaries=False):
         f = dict(order="F")
+        self.Phat = np.zeros((I, K), **f) if (summaries and R > 0) else None
+        self.Ehat = np.zeros((K, J), **f) if (summaries and R > 0) else None
         self.Zs = np.zeros((I, J, K, 1), **f) if (keep_par and want_Z and R > 0) else None
         self.Ps = np.zeros((I, K, R), **f) if samples else None
         self.Es = np.zeros((K, J, R), **f) if samples else None
@@ -92,7 +96,7 @@ class _Buffers:
 
     def struct(self):
         o = Outputs()
-        for name in ("Zs", "Ps", "Es", "Aps", "Aes", "Bps", "Bes", "loglik", "bic", "P", "E", "Ap", "Bp", "Ae", "Be"):
+        for name in ("Zs", "Ps", "Es", "Aps", "Aes", "Bps", "Bes", "loglik", "bic", "P", "E", "Ap", "Bp", "Ae", "Be", "Phat", "Ehat"):
             setattr(o, name, _ptr(getattr(self, name)))
         o.Zin = self.Zin.ctypes.data_as(ip)
         o.Znj = self.Znj.ctypes.data_as(ip)
@@ -107,6 +111,7 @@ class _Buffers:
         res.loglik, res.bic = self.loglik, self.bic
         res.state = dict(P=self.P, E=self.E, Ap=self.Ap, Bp=self.Bp, Ae=self.Ae, Be=self.Be)
         res.Zin, res.Znj = self.Zin, self.Znj
+        res.Phat, res.Ehat = self.Phat, self.Ehat
         res.seed = seed
         return res
 
@@ -179,7 +184,7 @@ class Chain:
         h = np.asarray(hyper, dtype=np.float64)
         check(_lib.lib().signer_chain_set_hyper(self._h, _ptr(h)))
 
-    def run(self, burn=0, eval=0, keep_par=False, fetch=True, want_Z=True, samples=True, forced_order=None):
+    def run(self, burn=0, eval=0, keep_par=False, fetch=True, want_Z=True, samples=True, forced_order=None, summaries=False):
         """burn sweeps without storage then eval sweeps with storage.  fetch=False leaves everything
         on the device (asynchronous; call sync())."""
         forced = _forced(forced_order, burn + eval)
@@ -187,7 +192,7 @@ class Chain:
         if not fetch:
             check(_lib.lib().signer_chain_run(self._h, burn, eval, int(keep_par), fptr, None))
             return None
-        buf = _Buffers(self.I, self.J, self.K, eval, bool(keep_par), want_Z=want_Z, samples=samples)
+        buf = _Buffers(self.I, self.J, self.K, eval, bool(keep_par), want_Z=want_Z, samples=samples, summaries=summaries)
         out = buf.struct()
         check(_lib.lib().signer_chain_run(self._h, burn, eval, int(keep_par), fptr, C.byref(out)))
         return buf.as_list(bool(keep_par), self.seed)

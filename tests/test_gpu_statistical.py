@@ -123,3 +123,32 @@ def test_synthetic_model_selection_recovers_planted_nsig(sg):
         med_ref[n] = float(np.median(r["bic"]))
     assert max(med_gpu, key=med_gpu.get) == max(med_ref, key=med_ref.get) == 3, (med_gpu, med_ref)
     assert res["Nsign"] == 3
+
+
+@pytest.mark.parametrize("R", [7, 64, 301])
+def test_device_summaries_equal_host_medians(sg, R):
+    """Phat/Ehat computed on the device (normalisation + medians over the eval samples) against NumPy on the same samples."""
+    M, W, _, _ = synth.cohort(24, 50, 3, burden=500.0, seed=1)
+    st = synth.init_state(24, 50, 3, seed=2)
+    with sg.Chain(M, W, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], synth.hyper_tuple(), seed=3) as c:
+        res = c.run(burn=20, eval=R, keep_par=False, fetch=True, summaries=True)
+    Ps, Es = res[2], res[3]
+    s = np.zeros((3, R))
+    for i in range(24):                                   # sequential sums like the device
+        s = s + Ps[i, :, :]
+    Phat = np.median(Ps / s[None, :, :], axis=2)
+    Ehat = np.median(Es * s[:, None, :], axis=2)
+    np.testing.assert_allclose(res.Phat, Phat, rtol=1e-15, atol=0)
+    np.testing.assert_allclose(res.Ehat, Ehat, rtol=1e-15, atol=0)
+    assert np.allclose(res.Phat.sum(axis=0), 1.0, atol=0.05)
+
+
+def test_ebayesnmf_device_summaries_match_signexp_path(sg):
+    M, W, _ = synth.breast21()
+    a = sg.eBayesNMF(M, W, 4, *[synth.HYPER_DEFAULT[k] for k in ("ap", "bp", "ae", "be", "lp", "le")], burn_it=100, eval_it=60,
+                     rng=np.random.default_rng(5))
+    b = sg.eBayesNMF(M, W, 4, *[synth.HYPER_DEFAULT[k] for k in ("ap", "bp", "ae", "be", "lp", "le")], burn_it=100, eval_it=60,
+                     rng=np.random.default_rng(5), keep_samples=False, device_summaries=True)
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-13)
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-13)
+    assert b[3] is None and np.array_equal(a[2], b[2])
