@@ -366,6 +366,15 @@ def main():
                     timing="second pass of %d burn-in sweeps with CUDA events around every launch" % n_prof,
                     note="issue/RNG-bound, working set L2-resident (SURVEY.md 8d): HBM fraction reported as defined; "
                          "see draws_per_s for the rate that binds")
+    # actual step-1 draws per sweep and the measured ceiling of the uniform-draw rate
+    chain.draw_counts(True)
+    n_cnt = 50
+    chain.run(burn=n_cnt, fetch=False)
+    n_cat, n_bin = chain.draw_counts(False)
+    from signer_b200 import _lib as _sl
+    import ctypes as _C
+    ceil = _C.c_double(0.0)
+    _sl.check(_sl.lib().signer_draw_ceiling(local, _C.byref(ceil)))
     b_sweep = 20.0 * I * J + 104.0 * K * (I + J)
     per_rank_sps = args.steps / (ms * 1e-3)
     kernels_ms = {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in prof.items()}
@@ -416,7 +425,14 @@ def main():
                     roofline_sweep=dict(algorithmic_bytes_per_sweep=b_sweep, achieved=b_sweep * per_rank_sps / 1e9, peak=peak,
                                         unit="GB/s", frac=b_sweep * per_rank_sps / 1e9 / peak),
                     kernel_ms=kernels_ms,
-                    draws_per_s=dict(binomial_upper_bound=per_rank_sps * I * J * (K - 1), gamma=per_rank_sps * 3 * K * (I + J)),
+                    draws_per_s=dict(step1_categorical=per_rank_sps * n_cat / n_cnt, step1_binomial=per_rank_sps * n_bin / n_cnt,
+                                     gamma=per_rank_sps * 3 * K * (I + J), mh_uniform=per_rank_sps * K * (I + J),
+                                     step1_draws_per_sweep=(n_cat + n_bin) / n_cnt,
+                                     reference_binomials_per_sweep_upper_bound=I * J * (K - 1),
+                                     ceiling_uniform_draws_per_s=ceil.value,
+                                     step1_fraction_of_ceiling=(n_cat + n_bin) / n_cnt / (z_ms * 1e-3) / ceil.value,
+                                     note="ceiling: Philox4x32-10 + 32-bit uniform + one inversion step per lane, no memory (signer_draw_ceiling); "
+                                          "fraction = step-1 draws per second of z_alloc_fused time / ceiling"),
                     cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     chain.close()

@@ -126,6 +126,9 @@ int signer_chain_profile(signer_chain *chain, int32_t enable, double ms[4], int6
 int64_t signer_chain_sweeps(const signer_chain *chain);
 /* Number of kernels this chain has launched so far (memsets and copies not counted). */
 int64_t signer_chain_launches(const signer_chain *chain);
+/* Step-1 draw counters: counts[0] = categorical draws of the direct method, counts[1] = conditional binomials, since the
+ * last call; enable != 0 switches counting on (one atomic per warp per launch), 0 off.  For the draw-rate report. */
+int signer_chain_draw_counts(signer_chain *chain, int32_t enable, uint64_t counts[2]);
 void signer_chain_destroy(signer_chain *chain);
 
 /* Candidates x chains over several GPUs of one box (replaces the multisession futures of
@@ -167,6 +170,10 @@ int signer_test_gamma(uint64_t seed, uint32_t sweep, uint32_t stream_id, const d
 /* host-side: scan order of one sweep (7 step ids) and raw Philox4x32-10 block */
 void signer_test_perm(uint64_t seed, uint32_t sweep, int32_t order[7]);
 void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Measured ceiling of the uniform-draw rate on `device`: a kernel that only generates Philox4x32-10
+ * blocks, turns each into four 32-bit uniforms and does one inversion step per uniform, no memory traffic. */
+int signer_draw_ceiling(int32_t device, double *draws_per_s);
 
 /* Thread-local text of the last error on this thread ("" if none). */
 const char *signer_last_error(void);

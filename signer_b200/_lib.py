@@ -55,7 +55,7 @@ class Task(C.Structure):
 EXPORTS = [
     "signer_gibbs_run", "signer_gibbs_run_sharded", "signer_chain_create", "signer_chain_set_stream", "signer_chain_set_hyper",
     "signer_chain_run", "signer_chain_sync", "signer_chain_fetch_state", "signer_chain_fetch_stats",
-    "signer_chain_profile", "signer_chain_sweeps", "signer_chain_launches", "signer_chain_destroy", "signer_gibbs_batch",
+    "signer_chain_profile", "signer_chain_sweeps", "signer_chain_launches", "signer_chain_draw_counts", "signer_draw_ceiling", "signer_chain_destroy", "signer_gibbs_batch",
     "signer_test_math", "signer_test_binomial", "signer_test_gamma", "signer_test_perm",
     "signer_test_philox", "signer_last_error", "signer_last_loop_ms", "signer_version", "signer_device_count",
 ]
@@ -97,6 +97,10 @@ def lib():
     L.signer_chain_sweeps.argtypes = [vp]
     L.signer_chain_launches.restype = C.c_int64
     L.signer_chain_launches.argtypes = [vp]
+    L.signer_chain_draw_counts.restype = C.c_int
+    L.signer_chain_draw_counts.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint64)]
+    L.signer_draw_ceiling.restype = C.c_int
+    L.signer_draw_ceiling.argtypes = [C.c_int32, dp]
     L.signer_chain_destroy.restype = None
     L.signer_chain_destroy.argtypes = [vp]
     L.signer_gibbs_batch.restype = C.c_int

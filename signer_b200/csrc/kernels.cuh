@@ -65,6 +65,7 @@ struct ZParams {
     unsigned long long base;
     int warp_smem;              // bytes of shared memory per warp
     int zin_smem;               // 1: accumulate Zin in shared memory per block
+    unsigned long long *draw_count;   // optional [2]: categorical draws (direct method), conditional binomials (chain)
     Key key;
     uint32_t sweep, stream;
 };
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
     int pow2 = 0;                                           // largest power of two <= ng
     if (ng > 0) { pow2 = 1; while (pow2 * 2 <= ng) pow2 *= 2; }
     const bool vec2 = (K & 1) == 0;
+    unsigned n_direct = 0, n_binom = 0;                     // this lane's draw counts (reported only on request)
 
     for (;;) {
         long long chunk = 0;
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
                         }
                         zc[cls * 32 + lane] += 1;
                         touched |= 1u << (cls & 31);
+                        ++n_direct;
                     }
                 }
                 const unsigned todo = (K <= 32) ? __reduce_or_sync(kFull, touched) : 0xffffffffu;
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
                             const uint32_t wt = (t & 2) ? ((t & 1) ? w4.w : w4.z) : ((t & 1) ? w4.y : w4.x);
                             const int z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, t, u32(wt), nrem, pp) : nrem;
                             nrem -= z;
+                            ++n_binom;
                             if (z) z_emit(p, zin_s, row, col, cur, z);
                         }
                         rem = rem - best;
@@ -235,6 +239,10 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
             if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                // degenerate probabilities
             __syncwarp();
         }
+    }
+    if (p.draw_count) {
+        const unsigned a = __reduce_add_sync(kFull, n_direct), b = __reduce_add_sync(kFull, n_binom);
+        if (lane == 0) { atomicAdd(p.draw_count, (unsigned long long)a); atomicAdd(p.draw_count + 1, (unsigned long long)b); }
     }
     if (zin_s) {
         __syncthreads();
@@ -670,6 +678,25 @@ __global__ void sum_shards(T *const *bufs, int n_shards, size_t n)
         for (int g = 1; g < n_shards; ++g) acc = acc + bufs[g][i];
         for (int g = 0; g < n_shards; ++g) bufs[g][i] = acc;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// draw-rate ceiling: Philox4x32-10 block -> four 32-bit uniforms -> four inversion steps
+// (compare against q^n, subtract), nothing read from memory; one store per thread keeps it alive
+// ------------------------------------------------------------------------------------------------
+__global__ void draw_ceiling(Key key, int iters, double r0, unsigned *sink)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned acc = 0;
+    double r = r0;
+    for (int it = 0; it < iters; ++it) {
+        const U4 w = philox4x32_10((uint32_t)it, e, 1u, 0u, key.k0, key.k1);
+        const double u0 = u32(w.x), u1 = u32(w.y), u2 = u32(w.z), u3 = u32(w.w);
+        acc += (u0 >= r) + (u1 >= r) + (u2 >= r) + (u3 >= r);
+        r = r0 + (u0 - r) * 1e-9;                          // keep r data-dependent so nothing is hoisted
+    }
+    if (acc == 0xffffffffu) sink[0] = acc;
+    if (e == 0) sink[1] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------

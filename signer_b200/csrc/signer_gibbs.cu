@@ -204,6 +204,7 @@ struct signer_chain {
     double *Zcube = nullptr;
     double *stats = nullptr;
     double *sumPs = nullptr, *sumEs = nullptr;   // full-length sample stores for the device-side summaries
+    unsigned long long *draw_count = nullptr;    // [2] device counters of step-1 draws (allocated on request)
     unsigned long long *tile_counter = nullptr;
     unsigned long long z_launches = 0;
     int z_grid = 0, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
@@ -231,7 +232,7 @@ struct signer_chain {
             cudaFree(Zin[b]); cudaFree(Znj[b]);
             free_ring(ring[b]);
         }
-        cudaFree(tile_counter);
+        cudaFree(tile_counter); cudaFree(draw_count);
         for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -290,6 +291,7 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     p.counter = c->tile_counter;
     p.base = c->z_launches * (unsigned long long)(c->n_chunks + c->z_grid * kZWarps);   // every warp overshoots once
     p.warp_smem = c->z_warp_smem; p.zin_smem = c->z_zin_smem;
+    p.draw_count = c->draw_count;
     p.key = c->key; p.sweep = sweep; p.stream = stream_id;
     if (zcube) CU(cudaMemsetAsync(zcube, 0, sizeof(double) * (size_t)c->I * c->J * c->K, c->stream));
     {
@@ -1132,6 +1134,43 @@ int signer_chain_profile(signer_chain *c, int32_t enable, double ms[4], int64_t 
 
 int64_t signer_chain_sweeps(const signer_chain *c) { return c ? c->sweeps_done : -1; }
 int64_t signer_chain_launches(const signer_chain *c) { return c ? c->launches : -1; }
+
+int signer_chain_draw_counts(signer_chain *c, int32_t enable, uint64_t counts[2])
+{
+    if (!c) return fail(SIGNER_ERR_ARG, "null chain");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (counts) { counts[0] = counts[1] = 0; }
+    if (c->draw_count && counts) CU(cudaMemcpy(counts, c->draw_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (enable && !c->draw_count) CU(cudaMalloc(&c->draw_count, 2 * sizeof(unsigned long long)));
+    if (c->draw_count) CU(cudaMemset(c->draw_count, 0, 2 * sizeof(unsigned long long)));
+    if (!enable && c->draw_count) { cudaFree(c->draw_count); c->draw_count = nullptr; }
+    return SIGNER_OK;
+}
+
+int signer_draw_ceiling(int32_t device, double *draws_per_s)
+{
+    g_err.clear();
+    if (!draws_per_s) return fail(SIGNER_ERR_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    unsigned *sink = nullptr;
+    CU(cudaMalloc(&sink, 2 * sizeof(unsigned)));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    const int iters = 2000, blocks = sms * 8, threads = 256;
+    draw_ceiling<<<blocks, threads>>>(Key{12345u, 678u}, 200, 0.37, sink);      // warm-up
+    CU(cudaEventRecord(a));
+    draw_ceiling<<<blocks, threads>>>(Key{12345u, 678u}, iters, 0.37, sink);
+    CU(cudaEventRecord(b));
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    *draws_per_s = 4.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    return SIGNER_OK;
+}
 
 void signer_chain_destroy(signer_chain *c) { delete c; }
 

@@ -223,6 +223,12 @@ class Chain:
     def sweeps(self):
         return int(_lib.lib().signer_chain_sweeps(self._h))
 
+    def draw_counts(self, enable=True):
+        """(categorical draws, conditional binomials) of step 1 since the last call; enable/disable counting."""
+        cnt = (C.c_uint64 * 2)()
+        check(_lib.lib().signer_chain_draw_counts(self._h, int(enable), cnt))
+        return int(cnt[0]), int(cnt[1])
+
     @property
     def launches(self):
         return int(_lib.lib().signer_chain_launches(self._h))
