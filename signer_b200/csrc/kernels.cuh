@@ -320,9 +320,21 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
             double tot = 0.0;
             for (int sh = 0; sh < p.n_shards; ++sh) {
                 const int s0 = (int)((long long)sh * p.n_seg / p.n_shards), s1 = (int)((long long)(sh + 1) * p.n_seg / p.n_shards);
+                // the adds are sequential (specified order); the loads are not: 16 partials are fetched at a time,
+                // the next 16 already in flight while the current ones are added
                 double part = 0.0;
-#pragma unroll 8
-                for (int s = s0; s < s1; ++s) part = part + p.corrE_part[(size_t)s * p.IK + e];
+                const double *src = p.corrE_part + e;
+                double cur[16], nxt[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) cur[u] = (s0 + u < s1) ? src[(size_t)(s0 + u) * p.IK] : 0.0;
+                for (int s = s0; s < s1; s += 16) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) nxt[u] = (s + 16 + u < s1) ? src[(size_t)(s + 16 + u) * p.IK] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) if (s + u < s1) part = part + cur[u];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+                }
                 tot = tot + part;
             }
             UStream us; us.init(p.key, p.sweep, kStP, (uint32_t)e);
