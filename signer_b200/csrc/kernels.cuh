@@ -266,24 +266,47 @@ SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, doubl
     return (kTiny < g) ? g : kTiny;
 }
 
-// steps 6/7 (src/gibbs_2.cpp:172-251): gamma proposal, log acceptance ratio, uniform accept
-__device__ __noinline__ double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var)
+// steps 6/7 (src/gibbs_2.cpp:172-251): gamma proposal, log acceptance ratio, uniform accept.
+// The three terms of the ratio that depend only on the current A -- lgamma(A+1), lgamma(A^2/v), log A -- are kept
+// in a per-element cache: A changes only when a proposal is accepted, and then its terms are exactly the
+// y-terms just evaluated.  Same operations on the same operands, so the result is bit-identical to
+// re-evaluating them (which is what the oracle does).
+struct ACache { double *lg1, *lg2, *lg; };     // lgamma(A+1), lgamma(A*A/var), log(A)
+
+__device__ __noinline__ double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var,
+                                        const ACache c, size_t ci)
 {
     UStream us; us.init(key, sweep, stream, e);
     const double shape = (A * A) / var;
     const double rate = A / var;
     const double g = gamma_draw(us, shape, rate);
     const double y = (kTiny < g) ? g : kTiny;
+    const double lgy1 = det_lgamma(y + 1), lgy2 = det_lgamma((y * y) / var), logy = det_log(y);
     const double lnp = (y - A) * (det_log(B) + det_log(X) - l)
-                     + det_lgamma(A + 1) - det_lgamma(y + 1)
-                     + det_lgamma((A * A) / var) - det_lgamma((y * y) / var)
+                     + c.lg1[ci] - lgy1
+                     + c.lg2[ci] - lgy2
                      + (((y * y) - (A * A)) / var) * det_log((A * y) / var)
-                     + det_log(y) - det_log(A);
+                     + logy - c.lg[ci];
     double pch = det_exp(lnp);
     if (X == 0) pch = (y < A) ? 1.0 : 0.0;
     double ub, um;
     us.pair(kAuxBlock, ub, um);
-    return (um <= pch) ? y : A;
+    if (um <= pch) {
+        c.lg1[ci] = lgy1; c.lg2[ci] = lgy2; c.lg[ci] = logy;
+        return y;
+    }
+    return A;
+}
+
+// (re)build the cache for a whole family: at chain creation and when var_ap / var_ae change
+__global__ void a_cache_init(const double *A, size_t n, double var, ACache c)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = A[i];
+    c.lg1[i] = det_lgamma(a + 1);
+    c.lg2[i] = det_lgamma((a * a) / var);
+    c.lg[i] = det_log(a);
 }
 
 // up to three step ids of one family, in permutation order, 4 bits each
@@ -303,6 +326,7 @@ struct PParams {
     const double *corrE_part;   // [n_seg][I*K] segment partials of W E'
     int n_seg, n_shards;
     double *Ps_slot, *Aps_slot, *Bps_slot;   // sample slots or null (src/gibbs_2.cpp:325-333)
+    ACache acache;
     Hyper h;
     Key key;
     uint32_t sweep;
@@ -344,7 +368,7 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
         } else if (op == 4) {
             Bp = update_b(p.key, p.sweep, kStBp, (uint32_t)e, Ap, P, p.h.ap, p.h.bp);
         } else if (op == 6) {
-            Ap = update_a(p.key, p.sweep, kStAp, (uint32_t)e, Ap, P, Bp, p.h.lp, p.h.var_ap);
+            Ap = update_a(p.key, p.sweep, kStAp, (uint32_t)e, Ap, P, Bp, p.h.lp, p.h.var_ap, p.acache, (size_t)e);
         }
     }
     p.P[e] = P; p.Ap[e] = Ap; p.Bp[e] = Bp;
@@ -369,6 +393,7 @@ struct EParams {
     double *corrE_part;         // [n_seg][I*K]
     int do_corrE;
     double *Es_slot, *Aes_slot, *Bes_slot;
+    ACache acache;
     Hyper h;
     Key key;
     uint32_t sweep;
@@ -391,7 +416,7 @@ __device__ __noinline__ void e_update_element(const EParams &p, size_t e, double
         } else if (op == 5) {
             Be = update_b(p.key, p.sweep, kStBe, eg, Ae, E, p.h.ae, p.h.be);
         } else if (op == 7) {
-            Ae = update_a(p.key, p.sweep, kStAe, eg, Ae, E, Be, p.h.le, p.h.var_ae);
+            Ae = update_a(p.key, p.sweep, kStAe, eg, Ae, E, Be, p.h.le, p.h.var_ae, p.acache, e);
         }
     }
     p.E[e] = E; p.Ae[e] = Ae; p.Be[e] = Be;

@@ -205,6 +205,7 @@ struct signer_chain {
     double *stats = nullptr;
     double *sumPs = nullptr, *sumEs = nullptr;   // full-length sample stores for the device-side summaries
     unsigned long long *draw_count = nullptr;    // [2] device counters of step-1 draws (allocated on request)
+    double *acache_p = nullptr, *acache_e = nullptr;   // [3][I*K], [3][K*J]: A-only terms of the MH ratios (kernels.cuh, ACache)
     unsigned long long *tile_counter = nullptr;
     unsigned long long z_launches = 0;
     int z_grid = 0, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
@@ -227,7 +228,7 @@ struct signer_chain {
         cudaSetDevice(device);
         if (own_stream) cudaStreamSynchronize(own_stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
-        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats, sumPs, sumEs}) cudaFree(p);
+        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats, sumPs, sumEs, acache_p, acache_e}) cudaFree(p);
         for (int b = 0; b < 2; ++b) {
             cudaFree(Zin[b]); cudaFree(Znj[b]);
             free_ring(ring[b]);
@@ -313,6 +314,7 @@ int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double
     if (c->n_shards > 1) { p.corrE_part = c->corrE_all; p.n_seg = c->n_shards; p.n_shards = c->n_shards; }
     else { p.corrE_part = c->corrE_part; p.n_seg = c->n_seg; p.n_shards = 1; }
     p.Ps_slot = Ps; p.Aps_slot = Aps; p.Bps_slot = Bps;
+    p.acache = ACache{c->acache_p, c->acache_p + c->nP, c->acache_p + 2 * c->nP};
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
     {
         ProfScope ps(c, 1);
@@ -332,6 +334,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     p.Znj = c->Znj[c->zcur]; p.corrE_part = c->corrE_part;
     p.do_corrE = do_corrE;
     p.Es_slot = Es; p.Aes_slot = Aes; p.Bes_slot = Bes;
+    p.acache = ACache{c->acache_e, c->acache_e + c->nE, c->acache_e + 2 * c->nE};
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
     {
         ProfScope ps(c, 2);
@@ -371,6 +374,14 @@ void prefault(double *p, size_t n_doubles)
     const size_t bytes = n_doubles * sizeof(double);
     for (size_t off = 0; off < bytes; off += 4096) b[off] = 0;
     if (bytes) b[bytes - 1] = 0;
+}
+
+int rebuild_a_cache(signer_chain *c)
+{
+    a_cache_init<<<(unsigned)((c->nP + 127) / 128), 128, 0, c->stream>>>(c->Ap, c->nP, c->h.var_ap, ACache{c->acache_p, c->acache_p + c->nP, c->acache_p + 2 * c->nP});
+    a_cache_init<<<(unsigned)((c->nE + 127) / 128), 128, 0, c->stream>>>(c->Ae, c->nE, c->h.var_ae, ACache{c->acache_e, c->acache_e + c->nE, c->acache_e + 2 * c->nE});
+    CU(cudaGetLastError());
+    return SIGNER_OK;
 }
 
 struct Slots { double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr; };
@@ -562,6 +573,9 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     CU(cudaMalloc(&c->tile_counter, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned long long), c->stream));
     CU(cudaMalloc(&c->stats, 8 * sizeof(double)));
+    CU(cudaMalloc(&c->acache_p, 3 * c->nP * sizeof(double)));
+    CU(cudaMalloc(&c->acache_e, 3 * c->nE * sizeof(double)));
+    ST(rebuild_a_cache(c.get()));
 
     // launch geometry
     c->n_batches = (data->n_cells + 31) / 32;
@@ -1067,7 +1081,9 @@ int signer_chain_set_stream(signer_chain *c, void *cuda_stream)
 int signer_chain_set_hyper(signer_chain *c, const double h[8])
 {
     if (!c || !h) return fail(SIGNER_ERR_ARG, "null argument");
+    const bool var_changed = (h[6] != c->h.var_ap) || (h[7] != c->h.var_ae);
     c->h = Hyper{h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
+    if (var_changed) { CU(cudaSetDevice(c->device)); ST(rebuild_a_cache(c)); }
     return SIGNER_OK;
 }
 
