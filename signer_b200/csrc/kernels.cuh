@@ -12,16 +12,17 @@
 // Random numbers are counter-based (draws.cuh), so the regrouping cannot change any draw.
 //
 // Device layouts: P,Ap,Bp,Zin I x K and E,Ae,Be,Znj K x J column-major exactly as the reference
-// (state and samples move with plain copies); M (int32) and W (fp64) row-major [I][Jp], Jp = J
-// rounded up to 32 and zero-padded, so that a warp whose lanes are 32 genomes reads them with
-// coalesced 128-bit loads.
+// (state and samples move with plain copies).  W (fp64) and M (int32, log-likelihood only) are
+// row-major [I][Jp], Jp = J rounded up to 32 and zero-padded: warps whose lanes are genomes read
+// coalesced rows, the W E' pass uses 128-bit loads.  z_alloc_fused does not read M: it walks a
+// count-sorted list of the non-zero cells built once per cohort (see K1).
 #pragma once
 #include "draws.cuh"
 
 namespace sg {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kEThreads = 256;    // e_family: 128 columns x 2 k-group lanes
+constexpr int kEThreads = 256;    // e_family: 128 genomes x 2 class pairs
 constexpr int kLLChunk = 32;      // rows per log-likelihood chunk
 
 struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
