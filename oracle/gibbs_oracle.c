@@ -61,6 +61,7 @@
 #define AUX_BLOCK 0xFFFFFFFFu
 #define BTRS_BLOCK0 0x1000u
 #define NDIRECT 32
+#define TAIL_BLOCK0 0x800u
 #define ORACLE_KMAX 128
 
 enum { ST_PERM = 0, ST_Z = 1, ST_P = 2, ST_E = 3, ST_BP = 4, ST_BE = 5, ST_AP = 6, ST_AE = 7, ST_ZINIT = 8 };
@@ -290,11 +291,12 @@ static int binomial_draw(const ustream *s, int kstep, int n, double pp)
         x = 0;
         if (u >= r) {
             double sr = p / q;
+            double a = sr * (nd + 1.0);              /* sr*(n-x+1)/x = a/x - sr */
             double xd = 0.0;
             while (u >= r && x < n) {
                 u = u - r;
                 x += 1; xd += 1.0;
-                r = (r * (sr * (nd - xd + 1.0))) * (1.0 / xd);
+                r = r * fma(a, 1.0 / xd, -sr);
             }
         }
     } else {
@@ -458,31 +460,58 @@ static void multinomial_cell(uint64_t seed, uint32_t sweep, uint32_t stream, int
         return;
     }
     /* Large counts: sequential conditional binomials as in R's rmultinom (zero-probability skip,
-     * pp<1 test, early exit at n<=0, remainder to the class visited last), but the classes are
-     * visited heaviest first: step t takes the not-yet-visited class with the largest P*E (ties:
-     * lowest index).  The multinomial law does not depend on the visiting order; the order makes
-     * the lanes of a GPU warp meet their expensive draws at the same step and lets the chain stop
-     * after the few classes that carry the mass. */
+     * pp<1 test, remainder to the class visited last), with two changes that leave the multinomial
+     * law untouched and suit a GPU warp:
+     *  (1) visiting order: classes sorted by the binary order of magnitude of P*E relative to S,
+     *      bucket d = min(7, expo(S) - expo(P*E)) ascending, ties lowest index first (heavy classes
+     *      first: the lanes of a warp meet their expensive draws together and the count is used up
+     *      after the few classes that carry the mass);
+     *  (2) the chain runs only while the remaining count exceeds NDIRECT; what is left is dealt to
+     *      the classes not yet visited by the direct method (draw d: word d&3 of block
+     *      TAIL_BLOCK0 + (d>>2); cumulative sums c_k in index order with the visited classes' P*E
+     *      set to zero, Sr = c_{K-1}; x = u*Sr; class = first k < K-1 with x < c_k, else K-1).
+     * Given the counts of the visited classes the rest is Multinomial(remaining, P*E of the rest). */
     double prob[ORACLE_KMAX];
-    unsigned char used[ORACLE_KMAX];
-    for (int m = 0; m < K; m++) { prob[m] = P[s + (size_t)I * m] * E[m + (size_t)K * g]; used[m] = 0; }
+    int order[ORACLE_KMAX];
+    int eS = (int)((d2u(S) >> 52) & 0x7ff);
+    int npos = 0;
+    for (int m = 0; m < K; m++) prob[m] = P[s + (size_t)I * m] * E[m + (size_t)K * g];
+    for (int d = 0; d < 8; d++)
+        for (int m = 0; m < K; m++) {
+            int dm = eS - (int)((d2u(prob[m]) >> 52) & 0x7ff);
+            if (dm > 7) dm = 7;
+            if (dm < 0) dm = 0;
+            if (dm == d) order[npos++] = m;
+        }
     double rem = S;
-    int cur = -1;
-    for (int t = 0; t < K; t++) {
-        double best = -1.0; cur = -1;
-        for (int m = 0; m < K; m++) if (!used[m] && prob[m] > best) { best = prob[m]; cur = m; }
-        used[cur] = 1;
-        if (t == K - 1) break;                       /* the last class takes the remainder */
+    int t = 0;
+    while (n > NDIRECT && t < K - 1) {
+        int cur = order[t];
+        double best = prob[cur];
         if (best != 0.0) {
             double pp = best / rem;
             int zz = (pp > 0.0 && pp < 1.0) ? binomial_draw(&us, t, n, pp) : n;
             z[cur * zs] = (double)zz;
             n -= zz;
         }
-        if (n <= 0) break;
         rem = rem - best;
+        t++;
     }
-    if (n > 0) z[cur * zs] += (double)n;
+    if (n <= 0) return;
+    if (t == K - 1) { z[order[K - 1] * zs] += (double)n; return; }
+    for (int j = 0; j < t; j++) prob[order[j]] = 0.0;           /* visited classes take no more */
+    double cum[ORACLE_KMAX];
+    double c = 0.0;
+    for (int m = 0; m < K; m++) { c = c + prob[m]; cum[m] = c; }
+    double Sr = c;
+    for (int d = 0; d < n; d++) {
+        double uq[4];
+        us_quad(&us, TAIL_BLOCK0 + ((uint32_t)d >> 2), uq);
+        double x = uq[d & 3] * Sr;
+        int cls = K - 1;
+        for (int m = 0; m < K - 1; m++) if (x < cum[m]) { cls = m; break; }
+        z[cls * zs] += 1.0;
+    }
 }
 
 /* step 1 -- src/gibbs_2.cpp:85-103 */

@@ -282,11 +282,12 @@ SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double
         double u = u_binv;
         if (u >= r) {
             const double sr = p / q;
+            const double a = sr * (nd + 1.0);         // sr*(n-x+1)/x = a/x - sr
             double xd = 0.0;
             while (u >= r && x < n) {
                 u = u - r;
                 x += 1; xd += 1.0;
-                r = (r * (sr * (nd - xd + 1.0))) * rcp_int(x, xd);
+                r = r * fma(a, rcp_int(x, xd), -sr);
             }
         }
     } else {

@@ -33,23 +33,41 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 // The counts M never change during a chain, so the non-zero cells are listed ONCE, sorted by count
 // (largest first; ties in genome-major order), and every launch walks that list: a warp takes 32
 // consecutive cells -- cells of (nearly) the same count, so the lanes run the same sampler with
-// the same trip count -- one thread per cell:
-//   * the lane stages its cell's K products P[i,k]*E[k,j] in shared memory (prob[k][lane]) while
-//     summing S = sum_k P E (fma chain) and, for small counts, the cumulative sums;
-//   * n <= 32 : direct method -- n categorical draws by binary search in the cumulative sums; the
-//     Philox block of four draws is generated warp-converged;
-//   * n  > 32 : R's rmultinom structure -- conditional binomials in lockstep (inversion below
-//     n*p < 30, BTRS above), each lane visiting its classes heaviest first, so the lanes meet their
-//     expensive draws together and the loop ends once the classes that carry the mass are done.
-// The class counts are reduced on the spot and Z is never written (except, on request, the final
-// sweep's cube for the reference's `Zs`): sum_j Z goes to a block-wide shared-memory Zin (integer
-// atomics, flushed once per block) and sum_i Z straight to L2 integer atomics, one per non-zero
-// count.  Work is claimed heaviest-first from a global counter, two batches at a time.
+// the same trip count -- one thread per cell.  Each lane owns one column of the warp's shared
+// memory: K doubles, K order bytes, K count bytes.
+//   * n <= 32 : direct method.  The lane stages the cumulative sums c_k of P[i,k]*E[k,j]; a draw is
+//     x = u*S and a branch-free two-level search (count the group ends <= x, then the thresholds of
+//     that group), four draws per Philox block searched together so their shared-memory loads overlap.
+//   * n  > 32 : the lane stages the products themselves, sorts the classes by binary order of
+//     magnitude (counting sort on the exponent distance to S: heavy classes first), runs R's
+//     conditional-binomial chain in that order while more than 32 mutations are left (inversion
+//     below n*p < 30, BTRS above), and deals the remainder to the unvisited classes by the direct
+//     method (linear scan in visiting order: the heavy classes come first).
+// Class counts of the direct draws are kept in the lane's count bytes (shared-memory adds without a
+// read-back) and flushed once per cell; Z is never written (except, on request, the final sweep's
+// cube for the reference's `Zs`): sum_j Z goes to a block-wide shared-memory Zin (integer atomics,
+// flushed once per block) and sum_i Z straight to L2 integer atomics.  Batches are claimed
+// heaviest-first from a global counter, one ahead of the batch being processed.
 // ------------------------------------------------------------------------------------------------
-constexpr int kZWarps = 8;        // warps per block (they share only the block's Zin accumulator)
-constexpr int kZChunk = 1;        // batches of 32 cells claimed at a time (finer claims balance the tail: 2 -> 1 measured)
+#ifndef SG_ZWARPS
+#define SG_ZWARPS 8
+#endif
+#ifndef SG_ZBLOCKS
+#define SG_ZBLOCKS 3
+#endif
+constexpr int kZWarps = SG_ZWARPS;   // warps per block (they share only the block's Zin accumulator)
+constexpr int kZChunk = 1;        // batches of 32 cells per claim
 constexpr int kNDirect = 32;      // largest count drawn by the direct method
 constexpr int kZinSmemMax = 40 * 1024;
+#ifndef SG_STAGE_UNROLL
+#define SG_STAGE_UNROLL 2
+#endif
+#ifndef SG_NTAIL
+#define SG_NTAIL 32
+#endif
+constexpr int kStageUnroll = SG_STAGE_UNROLL;
+constexpr int kNTail = SG_NTAIL;      // a chain stops once this few mutations are left; they are dealt by the direct method
+constexpr uint32_t kTailBlock0 = 0x800u;   // first Philox block of the direct draws that finish a chain
 
 struct ZParams {
     int I, J, K;
@@ -71,11 +89,14 @@ struct ZParams {
     uint32_t sweep, stream;
 };
 
-// per warp: prob [K][32] f64, cum4 [ceil((K-1)/4)][32] f64, zc [K][32] u8 ; per block: Zin [I*K] i32
-inline int z_groups(int K) { return (K - 1 + 3) / 4; }
+// per warp: buf [R][32] f64 (cumulative sums or products; R = K rounded up so that the thresholds c_0..c_{K-2} are
+// followed by at least one +inf pad and fill whole groups of four), ord [K][32] u8, zc [ceil(K/4)][32] u32 ; per block: Zin [I*K] i32
+__host__ __device__ inline int z_groups(int K) { return (K - 1) / 4 + 1; }
+__host__ __device__ inline int z_rows(int K) { return 4 * z_groups(K); }
+inline int z_words(int K) { return (K + 3) / 4; }
 inline size_t z_smem_bytes_per_warp(int K)
 {
-    return (size_t)8 * ((size_t)K * 32 + (size_t)z_groups(K) * 32) + ((size_t)K * 32 + 7) / 8 * 8;
+    return (size_t)8 * z_rows(K) * 32 + ((size_t)K * 32 + 7) / 8 * 8 + (size_t)z_words(K) * 32 * 4;
 }
 
 SG_D void z_emit(const ZParams &p, int *zin_s, int row, int col, int k, int z)
@@ -83,20 +104,119 @@ SG_D void z_emit(const ZParams &p, int *zin_s, int row, int col, int k, int z)
     if (zin_s) atomicAdd(zin_s + row + p.I * k, z);
     else atomicAdd(p.Zin + (size_t)row + (size_t)p.I * k, z);
     atomicAdd(p.Znj + (size_t)k + (size_t)p.K * col, z);
-    if (p.Zcube) p.Zcube[(size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k)] = (double)z;     // the shard's own cube
+    if (p.Zcube) p.Zcube[(size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k)] += (double)z;     // the shard's own cube
 }
 
-__global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p)
+// Classes of four direct draws on one column c of cumulative sums: class = first k < K-1 with x < c_k, else K-1.
+// The column holds c_0..c_{K-2} followed by +inf up to a multiple of four rows (so "else K-1" needs no special case).
+// Branch-free two-level search: count the group ends (every fourth row) <= x -- loaded once for the four draws, or
+// passed in registers (ge) when the caller keeps them across rounds -- then the first three rows of that group.
+// NG > 0: the number of groups at compile time; NG = 0: run-time ng.
+template <int NG>
+SG_D void z_search4(const double *c, int ng, const double *ge, double x0, double x1, double x2, double x3,
+                    int &c0, int &c1, int &c2, int &c3)
+{
+    int g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+    if (NG > 0) {
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) {
+            const double e = ge ? ge[gg] : c[(4 * gg + 3) * 32];
+            g0 += (e <= x0) ? 1 : 0; g1 += (e <= x1) ? 1 : 0; g2 += (e <= x2) ? 1 : 0; g3 += (e <= x3) ? 1 : 0;
+        }
+    } else {
+        for (int gg = 0; gg < ng; ++gg) {
+            const double e = c[(4 * gg + 3) * 32];
+            g0 += (e <= x0) ? 1 : 0; g1 += (e <= x1) ? 1 : 0; g2 += (e <= x2) ? 1 : 0; g3 += (e <= x3) ? 1 : 0;
+        }
+    }
+    const double *a0 = c + g0 * 128, *a1 = c + g1 * 128, *a2 = c + g2 * 128, *a3 = c + g3 * 128;
+    const double v00 = a0[0], v01 = a0[32], v02 = a0[64], v10 = a1[0], v11 = a1[32], v12 = a1[64];
+    const double v20 = a2[0], v21 = a2[32], v22 = a2[64], v30 = a3[0], v31 = a3[32], v32 = a3[64];
+    c0 = 4 * g0 + ((v00 <= x0) ? 1 : 0) + ((v01 <= x0) ? 1 : 0) + ((v02 <= x0) ? 1 : 0);
+    c1 = 4 * g1 + ((v10 <= x1) ? 1 : 0) + ((v11 <= x1) ? 1 : 0) + ((v12 <= x1) ? 1 : 0);
+    c2 = 4 * g2 + ((v20 <= x2) ? 1 : 0) + ((v21 <= x2) ? 1 : 0) + ((v22 <= x2) ? 1 : 0);
+    c3 = 4 * g3 + ((v30 <= x3) ? 1 : 0) + ((v31 <= x3) ? 1 : 0) + ((v32 <= x3) ? 1 : 0);
+}
+
+SG_D void z_count(unsigned *zc, int cls) { atomicAdd(zc + (cls >> 2) * 32, 1u << ((cls & 3) * 8)); }
+
+// the direct method for one batch: lane draws nn (0 for lanes that take no part) classes, four per Philox block;
+// draw t uses word t&3 of block t>>2 of the lane's stream.  The group ends stay in registers for the whole cell.
+template <int NG>
+SG_D void z_direct(const double *buf, unsigned *zc, const UStream &us, int ng, int nn, int tmax, double Sd)
+{
+    double ge[NG > 0 ? NG : 1];
+    if (NG > 0) {
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) ge[gg] = buf[(4 * gg + 3) * 32];
+    }
+    for (int t0 = 0; t0 < tmax; t0 += 4) {
+        const U4 w4 = us.words((uint32_t)t0 >> 2);                              // converged: once per four draws
+        int c0, c1, c2, c3;
+        z_search4<NG>(buf, ng, NG > 0 ? ge : nullptr, u32(w4.x) * Sd, u32(w4.y) * Sd, u32(w4.z) * Sd, u32(w4.w) * Sd, c0, c1, c2, c3);
+        if (t0 < nn) z_count(zc, c0);
+        if (t0 + 1 < nn) z_count(zc, c1);
+        if (t0 + 2 < nn) z_count(zc, c2);
+        if (t0 + 3 < nn) z_count(zc, c3);
+    }
+}
+
+// the direct draws that finish the chains of one batch, shared by the warp: the cells' Philox blocks (four draws
+// each) are dealt round-robin to the lanes, whoever owns the cell -- a lane reads the owner's column of shared
+// memory and adds to the owner's count bytes.  incl/excl: running totals of the lanes' block counts.
+template <int NG>
+SG_D void z_tail(const double *buf, unsigned *zc, const ZParams &p, int lane, int ng, int incl, int excl, int utot, int nrem,
+                 double Sr, uint32_t elem)
+{
+    for (int ub = 0; ub < utot; ub += 32) {
+        const int g = min(ub + lane, utot - 1);
+        const bool act = ub + lane < utot;
+        int o = 0;                                                             // owner: the first lane with incl > g
+#pragma unroll
+        for (int sft = 16; sft; sft >>= 1) { const int v = __shfl_sync(kFull, incl, o + sft - 1); if (v <= g) o += sft; }
+        const int b = g - __shfl_sync(kFull, excl, o);
+        const int nr_o = __shfl_sync(kFull, nrem, o);
+        const double Sr_o = __shfl_sync(kFull, Sr, o);
+        const uint32_t elem_o = __shfl_sync(kFull, elem, o);
+        const U4 w = philox4x32_10(kTailBlock0 + (uint32_t)b, elem_o, p.stream, p.sweep, p.key.k0, p.key.k1);
+        const int nd = act ? min(4, nr_o - 4 * b) : 0;                         // draws of this block
+        const double *buf_o = buf + (o - lane);
+        unsigned *zc_o = zc + (o - lane);
+        int c0, c1, c2, c3;
+        z_search4<NG>(buf_o, ng, nullptr, u32(w.x) * Sr_o, u32(w.y) * Sr_o, u32(w.z) * Sr_o, u32(w.w) * Sr_o, c0, c1, c2, c3);
+        if (nd > 0) z_count(zc_o, c0);
+        if (nd > 1) z_count(zc_o, c1);
+        if (nd > 2) z_count(zc_o, c2);
+        if (nd > 3) z_count(zc_o, c3);
+    }
+}
+
+// run F<NG>(args) with NG = ng when ng <= 8 (K <= 32), else the run-time version
+#define SG_DISPATCH_NG(ng, F, ...)                                                                     \
+    switch (ng) {                                                                                       \
+    case 1: F<1>(__VA_ARGS__); break; case 2: F<2>(__VA_ARGS__); break; case 3: F<3>(__VA_ARGS__); break; \
+    case 4: F<4>(__VA_ARGS__); break; case 5: F<5>(__VA_ARGS__); break; case 6: F<6>(__VA_ARGS__); break; \
+    case 7: F<7>(__VA_ARGS__); break; case 8: F<8>(__VA_ARGS__); break; default: F<0>(__VA_ARGS__); break; \
+    }
+
+#ifdef SG_Z_TIMING      // experiments only: cycles each batch of the last launch took (its warp's wall clock)
+__device__ unsigned g_z_batch_cycles[1 << 16];
+#endif
+
+SG_D int z_expo(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
+
+__global__ void __launch_bounds__(32 * kZWarps, SG_ZBLOCKS) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int I = p.I, J = p.J, K = p.K;
     unsigned char *base = smem_raw + (size_t)warp * p.warp_smem;
-    const int ng = (K - 1 + 3) / 4;                         // groups of four thresholds
-    double *prob = reinterpret_cast<double *>(base);        // [K][32] this lane's P[i,k]*E[k,j]
-    double *cum4 = prob + K * 32;                           // cumulative sums at the end of each group
-    unsigned char *zc = reinterpret_cast<unsigned char *>(cum4 + ng * 32);
+    double *buf = reinterpret_cast<double *>(base) + lane;              // this lane's column: buf[k * 32]
+    const int ng = z_groups(K), R = 4 * ng;                             // groups of four thresholds, rows of buf
+    unsigned char *ord = base + (size_t)8 * R * 32 + lane;              // ord[t * 32]: class visited at step t
+    unsigned *zc = reinterpret_cast<unsigned *>(base + (size_t)8 * R * 32 + ((size_t)K * 32 + 7) / 8 * 8) + lane;   // zc[w * 32]: counts of classes 4w..4w+3
     int *zin_s = p.zin_smem ? reinterpret_cast<int *>(smem_raw + (size_t)kZWarps * p.warp_smem) : nullptr;
+    const int nw = (K + 3) / 4;
 
     // zero the other half of the ping-pong for the next launch
     {
@@ -108,138 +228,178 @@ __global__ void __launch_bounds__(32 * kZWarps, 3) z_alloc_fused(const ZParams p
         for (int i = tid; i < I * K; i += 32 * kZWarps) zin_s[i] = 0;
         __syncthreads();
     }
-    for (int k = 0; k < K; ++k) zc[k * 32 + lane] = 0;      // invariant: all zero between cells
-    int pow2 = 0;                                           // largest power of two <= ng
-    if (ng > 0) { pow2 = 1; while (pow2 * 2 <= ng) pow2 *= 2; }
+    for (int w = 0; w < nw; ++w) zc[w * 32] = 0;            // invariant: all zero between cells
     const bool vec2 = (K & 1) == 0;
     unsigned n_direct = 0, n_binom = 0;                     // this lane's draw counts (reported only on request)
 
-    for (;;) {
-        long long chunk = 0;
-        if (lane == 0) chunk = (long long)(atomicAdd(p.counter, 1ULL) - p.base);
-        chunk = __shfl_sync(kFull, chunk, 0);
-        if (chunk * kZChunk >= p.n_batches) break;
-        for (int bb = 0; bb < kZChunk; ++bb) {
-            const int batch = (int)chunk * kZChunk + bb;
-            if (batch >= p.n_batches) break;
-            const int cell = batch * 32 + lane;
-            const bool valid = cell < p.n_cells;
-            const int n = valid ? p.cell_n[cell] : 0;
-            const int row = valid ? (int)p.cell_row[cell] : 0;
-            const int col = valid ? p.cell_col[cell] : 0;
-            const bool maybe_small = __any_sync(kFull, valid && n <= kNDirect);
+    // batches are claimed from a global counter.  While a batch of small counts runs, the claim for the next one is
+    // already in flight; a batch of large counts claims its successor when it is done (nothing is held back from
+    // idle warps while a long chain runs)
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    int cur = 0, pend = 0;
+    if (lane == 0) cur = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+    cur = __shfl_sync(kFull, cur, 0);
+    while (cur < p.n_batches) {
+#ifdef SG_Z_TIMING
+        const long long t_begin = clock64();
+        const int t_batch = cur;
+#endif
+        const int cell = cur * 32 + lane;
+        const int n = cell < p.n_cells ? p.cell_n[cell] : 0;
+        const int row = cell < p.n_cells ? (int)p.cell_row[cell] : 0;
+        const int col = cell < p.n_cells ? p.cell_col[cell] : 0;
+        const bool early = __shfl_sync(kFull, n, 0) <= kNDirect;               // lane 0 holds the batch's largest count
+        if (early && lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+        const bool valid = n > 0;                           // listed cells have n >= 1; lanes past the end of the list have 0
+        const bool bycount_small = n <= kNDirect;
 
-            // stage P[i,.] o E[.,j]; S = fma chain; cumulative sums for the direct method
-            const double *Pr = p.P + row;
-            const double *Ec = p.E + (size_t)K * col;
-            double S = 0.0, c = 0.0;
-            if (vec2) {
-                for (int k = 0; k < K; k += 2) {
-                    const double2 ee = *reinterpret_cast<const double2 *>(Ec + k);
-                    const double p0 = __ldg(Pr + (size_t)I * k), p1 = __ldg(Pr + (size_t)I * (k + 1));
-                    S = fma(p0, ee.x, S);
-                    S = fma(p1, ee.y, S);
-                    const double q0 = p0 * ee.x, q1 = p1 * ee.y;
-                    prob[k * 32 + lane] = q0;
-                    prob[(k + 1) * 32 + lane] = q1;
-                    if (maybe_small) {
-                        if (k < K - 1) { c = c + q0; if ((k & 3) == 3 || k == K - 2) cum4[(k >> 2) * 32 + lane] = c; }
-                        if (k + 1 < K - 1) { c = c + q1; if (((k + 1) & 3) == 3 || k + 1 == K - 2) cum4[((k + 1) >> 2) * 32 + lane] = c; }
-                    }
+        // stage P[i,.] o E[.,j]: S = fma chain; cumulative sums (direct method) or the products (chain)
+        const double *Pr = p.P + row;
+        const double *Ec = p.E + (size_t)K * col;
+        double S = 0.0, c = 0.0;
+        {
+            int k = 0;
+#pragma unroll kStageUnroll
+            for (; k + 4 <= K; k += 4) {                    // four classes per round, their loads issued together
+                double e0, e1, e2, e3;
+                if (vec2) {
+                    const double2 a = *reinterpret_cast<const double2 *>(Ec + k), b = *reinterpret_cast<const double2 *>(Ec + k + 2);
+                    e0 = a.x; e1 = a.y; e2 = b.x; e3 = b.y;
+                } else {
+                    e0 = Ec[k]; e1 = Ec[k + 1]; e2 = Ec[k + 2]; e3 = Ec[k + 3];
                 }
-            } else {
-                for (int k = 0; k < K; ++k) {
-                    const double ee = Ec[k], pe = __ldg(Pr + (size_t)I * k);
-                    S = fma(pe, ee, S);
-                    const double q0 = pe * ee;
-                    prob[k * 32 + lane] = q0;
-                    if (maybe_small && k < K - 1) { c = c + q0; if ((k & 3) == 3 || k == K - 2) cum4[(k >> 2) * 32 + lane] = c; }
-                }
+                const double p0 = __ldg(Pr + (size_t)I * k), p1 = __ldg(Pr + (size_t)I * (k + 1));
+                const double p2 = __ldg(Pr + (size_t)I * (k + 2)), p3 = __ldg(Pr + (size_t)I * (k + 3));
+                S = fma(p0, e0, S); S = fma(p1, e1, S); S = fma(p2, e2, S); S = fma(p3, e3, S);
+                const double q0 = p0 * e0, q1 = p1 * e1, q2 = p2 * e2, q3 = p3 * e3;
+                const double c0 = c + q0, c1 = c0 + q1, c2 = c1 + q2;
+                c = c2 + q3;
+                buf[k * 32] = bycount_small ? c0 : q0;
+                buf[(k + 1) * 32] = bycount_small ? c1 : q1;
+                buf[(k + 2) * 32] = bycount_small ? c2 : q2;
+                buf[(k + 3) * 32] = bycount_small ? c : q3;
             }
-            const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
-            const bool small = valid && ok && n <= kNDirect;
-            int nrem = (valid && ok && n > kNDirect) ? n : 0;
-            const int nlast = (valid && !ok) ? n : 0;       // degenerate probabilities: all to the last class
-            UStream us;
-            us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * (col + p.col0)));
-
-            // ---- direct method
-            if (__any_sync(kFull, small)) {
-                const int tmax = __reduce_max_sync(kFull, small ? n : 0);
-                unsigned touched = 0;
-                U4 w4 = U4{0, 0, 0, 0};
-                for (int t = 0; t < tmax; ++t) {
-                    if ((t & 3) == 0) w4 = us.words((uint32_t)t >> 2);        // converged: once per four draws
-                    if (small && t < n) {
-                        const uint32_t wt = (t & 2) ? ((t & 1) ? w4.w : w4.z) : ((t & 1) ? w4.y : w4.x);
-                        const double x = u32(wt) * S;
-                        int g = 0;                                            // number of group ends <= x
-                        for (int step = pow2; step; step >>= 1) {
-                            const int np = g + step;
-                            if (np <= ng && cum4[(np - 1) * 32 + lane] <= x) g = np;
-                        }
-                        int cls = K - 1;
-                        if (g < ng) {                                         // x < cum4[g]: finish inside the group
-                            double cc = g ? cum4[(g - 1) * 32 + lane] : 0.0;
-                            cls = 4 * g;
-                            for (;;) {
-                                cc = cc + prob[cls * 32 + lane];
-                                if (x < cc || cls >= K - 2) break;
-                                ++cls;
-                            }
-                        }
-                        zc[cls * 32 + lane] += 1;
-                        touched |= 1u << (cls & 31);
-                        ++n_direct;
-                    }
-                }
-                const unsigned todo = (K <= 32) ? __reduce_or_sync(kFull, touched) : 0xffffffffu;
-                for (int k = 0; k < K; ++k) {
-                    if (K <= 32 && !((todo >> k) & 1u)) continue;
-                    const int z = zc[k * 32 + lane];
-                    if (z) {
-                        zc[k * 32 + lane] = 0;
-                        z_emit(p, zin_s, row, col, k, z);
-                    }
-                }
+            for (; k < K; ++k) {
+                const double ee = Ec[k], pe = __ldg(Pr + (size_t)I * k);
+                S = fma(pe, ee, S);
+                const double q0 = pe * ee;
+                c = c + q0;
+                buf[k * 32] = bycount_small ? c : q0;
             }
-
-            // ---- conditional-binomial chain for the large counts: classes visited heaviest first
-            // (running argmax of this lane's products; a visited class is marked with -1)
-            if (__any_sync(kFull, nrem > 0)) {
-                double rem = S;
-                U4 w4 = U4{0, 0, 0, 0};
-                for (int t = 0; t < K; ++t) {
-                    if (!__any_sync(kFull, nrem > 0)) break;
-                    double best = -1.0;
-                    int cur = 0;
-                    for (int k = 0; k < K; ++k) {
-                        const double v = prob[k * 32 + lane];
-                        if (v > best) { best = v; cur = k; }
-                    }
-                    prob[cur * 32 + lane] = -1.0;
-                    if (t == K - 1) {                                           // the last class takes the remainder
-                        if (nrem > 0) z_emit(p, zin_s, row, col, cur, nrem);
-                        nrem = 0;
-                        break;
-                    }
-                    if ((t & 3) == 0) w4 = us.words((uint32_t)t >> 2);          // converged: once per four binomials
-                    if (nrem > 0) {
-                        if (best != 0.0) {
-                            const double pp = best / rem;
-                            const uint32_t wt = (t & 2) ? ((t & 1) ? w4.w : w4.z) : ((t & 1) ? w4.y : w4.x);
-                            const int z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, t, u32(wt), nrem, pp) : nrem;
-                            nrem -= z;
-                            ++n_binom;
-                            if (z) z_emit(p, zin_s, row, col, cur, z);
-                        }
-                        rem = rem - best;
-                    }
-                }
-            }
-            if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                // degenerate probabilities
-            __syncwarp();
+            if (bycount_small) for (k = K - 1; k < R; ++k) buf[k * 32] = kInf;   // c_{K-1} is not a threshold
         }
+        const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
+        const bool small = valid && ok && bycount_small;
+        int nrem = (valid && ok && !bycount_small) ? n : 0;
+        const int nlast = (valid && !ok) ? n : 0;           // degenerate probabilities: all to the last class
+        UStream us;
+        us.init(p.key, p.sweep, p.stream, (uint32_t)(row + I * (col + p.col0)));
+
+        // ---- direct method: draw t uses word t&3 of block t>>2
+        if (__any_sync(kFull, small)) {
+            const int tmax = __reduce_max_sync(kFull, small ? n : 0);
+            const int nn = small ? n : 0;
+            const double Sd = small ? S : -1.0;                                // other lanes search with x < 0: class 0, discarded
+            SG_DISPATCH_NG(ng, z_direct, buf, zc, us, ng, nn, tmax, Sd)
+            n_direct += (unsigned)nn;
+        }
+
+        // ---- large counts
+        if (__any_sync(kFull, nrem > 0)) {
+            // visiting order: counting sort of the classes by d = min(7, expo(S) - expo(P*E)), ties by index
+            if (nrem > 0) {
+                const int eS = z_expo(S);
+                unsigned lo = 0, hi = 0;                                       // eight byte-wide bucket counters
+                for (int k = 0; k < K; ++k) {
+                    const int d = max(0, min(7, eS - z_expo(buf[k * 32])));
+                    if (d < 4) lo += 1u << (8 * d); else hi += 1u << (8 * (d - 4));
+                }
+                const unsigned tot_lo = (lo * 0x01010101u) >> 24;
+                unsigned lo_off = lo * 0x01010100u;                            // byte b: number of classes in buckets below b
+                unsigned hi_off = hi * 0x01010100u + tot_lo * 0x01010101u;
+                for (int k = 0; k < K; ++k) {
+                    const int d = max(0, min(7, eS - z_expo(buf[k * 32])));
+                    unsigned pos;
+                    if (d < 4) { pos = (lo_off >> (8 * d)) & 255u; lo_off += 1u << (8 * d); }
+                    else { pos = (hi_off >> (8 * (d - 4))) & 255u; hi_off += 1u << (8 * (d - 4)); }
+                    ord[pos * 32] = (unsigned char)k;
+                }
+            }
+            // conditional binomials in visiting order while more than kNDirect mutations are left;
+            // binomial t uses word t&3 of block t>>2
+            double rem = S;
+            int tl = 0;                                                        // classes this lane has visited
+            U4 w4 = U4{0, 0, 0, 0};
+            for (int t = 0; t < K - 1; ++t) {
+                if (!__any_sync(kFull, nrem > kNTail)) break;
+                if ((t & 3) == 0) w4 = us.words((uint32_t)t >> 2);             // converged: once per four binomials
+                if (nrem > kNTail) {
+                    const int cur = ord[t * 32];
+                    const double best = buf[cur * 32];
+                    if (best != 0.0) {
+                        const double pp = best / rem;
+                        const uint32_t wt = (t & 2) ? ((t & 1) ? w4.w : w4.z) : ((t & 1) ? w4.y : w4.x);
+                        const int z = (pp > 0.0 && pp < 1.0) ? binomial_draw(us, t, u32(wt), nrem, pp) : nrem;
+                        nrem -= z;
+                        ++n_binom;
+                        if (z) z_emit(p, zin_s, row, col, cur, z);
+                    }
+                    rem = rem - best;
+                    tl = t + 1;
+                }
+            }
+            if (nrem > 0 && tl == K - 1) {                                      // only the class visited last is left
+                z_emit(p, zin_s, row, col, ord[(K - 1) * 32], nrem);
+                nrem = 0;
+            }
+            // the remainder goes to the unvisited classes by the direct method: the lane's column becomes the
+            // cumulative sums in index order with the visited classes zeroed; draw d of a cell uses word d&3 of
+            // block kTailBlock0 + (d>>2) of the cell's stream and the same search as the small counts.  The warp
+            // shares this work: the cells' Philox blocks (four draws each) are dealt round-robin to the lanes,
+            // whoever owns the cell -- a lane reads the owner's column of shared memory and adds to the owner's
+            // count bytes.
+            if (__any_sync(kFull, nrem > 0)) {
+                double Sr = 0.0;
+                if (nrem > 0) {
+                    for (int t = 0; t < tl; ++t) buf[(int)ord[t * 32] * 32] = 0.0;
+                    for (int k = 0; k < K; ++k) {
+                        Sr = Sr + buf[k * 32];
+                        buf[k * 32] = Sr;
+                    }
+                    for (int k = K - 1; k < R; ++k) buf[k * 32] = kInf;
+                }
+                const int units = (nrem + 3) >> 2;
+                int incl = units;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                const int excl = incl - units;
+                const int utot = __shfl_sync(kFull, incl, 31);
+                const uint32_t elem = (uint32_t)(row + I * (col + p.col0));
+                __syncwarp();
+                SG_DISPATCH_NG(ng, z_tail, buf, zc, p, lane, ng, incl, excl, utot, nrem, Sr, elem)
+                __syncwarp();
+                n_direct += (unsigned)nrem;
+            }
+        }
+
+        // ---- flush the direct draws' class counts
+        for (int w = 0; w < nw; ++w) {
+            const unsigned v = zc[w * 32];
+            if (v) {
+                zc[w * 32] = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int z = (int)((v >> (8 * b)) & 255u);
+                    if (z) z_emit(p, zin_s, row, col, 4 * w + b, z);
+                }
+            }
+        }
+        if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                    // degenerate probabilities
+#ifdef SG_Z_TIMING
+        if (lane == 0 && t_batch < (1 << 16)) g_z_batch_cycles[t_batch] = (unsigned)(clock64() - t_begin);
+#endif
+        if (!early && lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+        cur = __shfl_sync(kFull, pend, 0);
     }
     if (p.draw_count) {
         const unsigned a = __reduce_add_sync(kFull, n_direct), b = __reduce_add_sync(kFull, n_binom);

@@ -68,6 +68,27 @@ struct DeviceData {
     }
 };
 
+// cells per batch of z_alloc_fused's work list for cells of count n (see upload_data); SIGNER_Z_WIDTHS="n:w,n:w,..."
+// (descending n) overrides the built-in grading for experiments
+int batch_width(int n)
+{
+    static const std::vector<std::pair<int, int>> grade = [] {
+        std::vector<std::pair<int, int>> g;
+        if (const char *e = std::getenv("SIGNER_Z_WIDTHS")) {
+            g.clear();
+            int a = 0, b = 0, used = 0;
+            while (std::sscanf(e, "%d:%d%n", &a, &b, &used) == 2) {
+                g.emplace_back(a, std::max(1, std::min(32, b)));
+                e += used;
+                if (*e == ',') ++e;
+            }
+        }
+        return g;
+    }();
+    for (const auto &g : grade) if (n >= g.first) return g.second;
+    return 32;
+}
+
 int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out, int col0 = 0,
                 int Jglobal = -1)
 {
@@ -94,43 +115,37 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
             w[(size_t)i * d->Jp + j] = wv;
             if (mi > 0) cells.push_back(i + I * j);
         }
-    // z_alloc_fused's work list (a private order: results do not depend on it): counting sort by
-    // count, largest first, ties keep the genome-major order
-    d->n_cells = (int)cells.size();
-    const size_t nc = std::max<size_t>(cells.size(), 1);
-    std::vector<unsigned short> crow(nc, 0);
-    std::vector<int> ccol(nc, 0), cn(nc, 0);
+    // z_alloc_fused's work list (a private order: results do not depend on it): the non-zero cells sorted by
+    // count, largest first (ties keep the genome-major order), cut into batches of 32 list entries = one warp
+    // round each.  batch_width() can give the heaviest cells narrower batches (the rest of the batch is padding,
+    // count 0); measured on B200 every such grading lost to plain 32-cell batches, so the default is none.
+    std::vector<unsigned short> crow;
+    std::vector<int> ccol, cn;
     {
-        std::vector<int> cnt(cells.size());
-        int nmax = 0;
-        for (size_t t = 0; t < cells.size(); ++t) {
+        const size_t nz = cells.size();
+        std::vector<int> cnt(nz);
+        for (size_t t = 0; t < nz; ++t) {
             const int i = cells[t] % I, j = cells[t] / I;
             cnt[t] = m[(size_t)i * d->Jp + j];
-            nmax = std::max(nmax, cnt[t]);
         }
-        std::vector<size_t> pos;
-        std::vector<int> keys;                       // distinct counts, descending
-        if (nmax <= (1 << 22)) {
-            std::vector<size_t> hist((size_t)nmax + 2, 0);
-            for (int v : cnt) hist[(size_t)v]++;
-            pos.assign((size_t)nmax + 2, 0);
-            size_t run = 0;
-            for (int v = nmax; v >= 1; --v) { pos[(size_t)v] = run; run += hist[(size_t)v]; }
-            for (size_t t = 0; t < cells.size(); ++t) {
-                const size_t dst = pos[(size_t)cnt[t]]++;
-                const int i = cells[t] % I, j = cells[t] / I;
-                crow[dst] = (unsigned short)i; ccol[dst] = j; cn[dst] = cnt[t];
+        std::vector<size_t> idx(nz);
+        for (size_t t = 0; t < nz; ++t) idx[t] = t;
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cnt[a] > cnt[b]; });
+        crow.reserve(nz + 4096); ccol.reserve(nz + 4096); cn.reserve(nz + 4096);
+        size_t t = 0;
+        while (t < nz) {
+            const int width = batch_width(cnt[idx[t]]);
+            int filled = 0;
+            for (; filled < width && t < nz; ++filled, ++t) {
+                const size_t e = idx[t];
+                crow.push_back((unsigned short)(cells[e] % I)); ccol.push_back(cells[e] / I); cn.push_back(cnt[e]);
             }
-        } else {
-            std::vector<size_t> idx(cells.size());
-            for (size_t t = 0; t < idx.size(); ++t) idx[t] = t;
-            std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cnt[a] > cnt[b]; });
-            for (size_t dst = 0; dst < idx.size(); ++dst) {
-                const size_t t = idx[dst];
-                crow[dst] = (unsigned short)(cells[t] % I); ccol[dst] = cells[t] / I; cn[dst] = cnt[t];
-            }
+            if (t < nz) for (; filled < 32; ++filled) { crow.push_back(0); ccol.push_back(0); cn.push_back(0); }
         }
     }
+    d->n_cells = (int)cn.size();
+    if (cn.empty()) { crow.push_back(0); ccol.push_back(0); cn.push_back(0); }
+    const size_t nc = cn.size();
     CU(cudaMalloc(&d->cell_row, nc * sizeof(unsigned short)));
     CU(cudaMalloc(&d->cell_col, nc * sizeof(int)));
     CU(cudaMalloc(&d->cell_n, nc * sizeof(int)));
@@ -177,6 +192,9 @@ int ensure_device_setup(int device)
     CU(cudaFuncGetAttributes(&fa, z_alloc_fused));
     g_z_dyn_smem_max[device] = optin - (int)fa.sharedSizeBytes;
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
+#ifdef SG_Z_CARVEOUT
+    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, SG_Z_CARVEOUT));
+#endif
     done[device] = true;
     return SIGNER_OK;
 }
@@ -1346,3 +1364,10 @@ void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 }
 
 } // extern "C"
+
+#ifdef SG_Z_TIMING
+extern "C" int signer_debug_batch_cycles(unsigned *out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, sg::g_z_batch_cycles, sizeof(unsigned) * (size_t)n);
+}
+#endif

@@ -1,4 +1,4 @@
-"""Golden vectors of the draw specification (tests/golden/spec_v5.npz, made by make_golden.py):
+"""Golden vectors of the draw specification (tests/golden/spec_v6.npz, made by make_golden.py):
 the oracle must reproduce them here on the CPU, the CUDA path on the GPU."""
 import ctypes as C
 import os
@@ -8,7 +8,7 @@ import pytest
 
 from helpers import assert_bits_equal
 
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spec_v5.npz"))
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spec_v6.npz"))
 STATE = ("P", "E", "Ap", "Bp", "Ae", "Be")
 
 
