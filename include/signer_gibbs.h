@@ -159,7 +159,7 @@ int signer_gibbs_run_sharded(const signer_problem *problem, const signer_state *
 
 /* Test hooks: the deterministic primitives of the draw specification evaluated ON THE DEVICE, so
  * tests can compare them bit for bit with the oracle.  n values each; fn: 0 log, 1 exp, 2 lgamma,
- * 3 ppnd16. */
+ * 3 the ziggurat normal of stream (seed 12345, sweep 0, stream 3, element i), attempt (uint32) x[i]. */
 int signer_test_math(int32_t fn, const double *x, double *y, int32_t n, int32_t device);
 /* binomial(n[i], p[i]) drawn as conditional binomial number `kstep` of stream (seed, sweep, stream_id, element=i) */
 int signer_test_binomial(uint64_t seed, uint32_t sweep, uint32_t stream_id, int32_t kstep, const int32_t *n,

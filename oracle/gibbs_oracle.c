@@ -54,6 +54,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "det_tables.h"
+
 #define ORACLE_SEG 128
 #define ORACLE_LLCHUNK 32
 #define BINV_MAX 30.0
@@ -126,14 +128,15 @@ static void us_block(const ustream *s, uint32_t block, double *u0, double *u1)
 static inline uint64_t d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 static inline double u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 
-/* log(x): argument reduction and minimax polynomial in the style of fdlibm's e_log.c
- * (Sun Microsystems, public algorithm), single evaluation formula, explicit fma Horner. */
+/* log(x), division-free: x = 2^k z with bits(z) in [OFF, OFF + 2^52) (z in [0.6875, 1.375)); a 128-entry table gives
+ * invc ~ 1/z and logc = -log(invc) for the run of bit patterns z falls in; r = fma(z, invc, -1) (|r| < 2^-7);
+ * log x = k ln2 + logc + log1p(r), log1p by its Taylor polynomial up to r^9, the leading terms summed in two pieces.
+ * (The scheme of table-driven logarithms, e.g. Tang 1990; the table is generated by scripts/make_det_tables.py.) */
+static const double log_tab[SG_LOG_N][2] = SG_LOG_TABLE;
+
 double oracle_log(double x)
 {
-    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
-        Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
-        Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-        Lg7 = 1.479819860511658591e-01;
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     uint64_t ux = d2u(x);
     int32_t hx = (int32_t)(ux >> 32);
     uint32_t lx = (uint32_t)ux;
@@ -144,20 +147,20 @@ double oracle_log(double x)
         k -= 54; x *= 0x1p54; ux = d2u(x); hx = (int32_t)(ux >> 32); lx = (uint32_t)ux;
     }
     if (hx >= 0x7ff00000) return x + x;
-    k += (hx >> 20) - 1023;
-    hx &= 0x000fffff;
-    int32_t i = (hx + 0x95f64) & 0x100000;
-    x = u2d(((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | lx);
-    k += (i >> 20);
-    double f = x - 1.0;
-    double s = f / (2.0 + f);
-    double dk = (double)k;
-    double z = s * s, w = z * z;
-    double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
-    double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
-    double R = t2 + t1;
-    double hfsq = 0.5 * f * f;
-    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    int32_t tmp = hx - (int32_t)SG_LOG_OFF_HI;
+    int i = (tmp >> 13) & (SG_LOG_N - 1);
+    k += tmp >> 20;                                        /* arithmetic shift */
+    double z = u2d(((uint64_t)(uint32_t)(hx - (tmp & (int32_t)0xfff00000)) << 32) | lx);
+    double invc = log_tab[i][0], logc = log_tab[i][1];
+    double r = fma(z, invc, -1.0);
+    double kd = (double)k;
+    double w = fma(kd, ln2_hi, logc);
+    double hi = w + r;
+    double lo = ((w - hi) + r) + kd * ln2_lo;
+    double q = fma(r, 1.0 / 9.0, -1.0 / 8.0);
+    q = fma(r, q, 1.0 / 7.0); q = fma(r, q, -1.0 / 6.0); q = fma(r, q, 1.0 / 5.0);
+    q = fma(r, q, -1.0 / 4.0); q = fma(r, q, 1.0 / 3.0); q = fma(r, q, -0.5);
+    return (lo + (r * r) * q) + hi;
 }
 
 /* exp(x): fdlibm e_exp.c style reduction x = k ln2 + r, rational form, unified formula. */
@@ -216,41 +219,6 @@ double oracle_lgamma(double x)
     double ser = r * fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, S7, S6), S5), S4), S3), S2), S1), S0);
     double lg = ((y - 0.5) * oracle_log(y) - y) + HALF_LOG_2PI + ser;
     return lg - corr;
-}
-
-/* Standard normal quantile: Wichura, Algorithm AS 241 (Appl. Statist. 37, 1988), routine PPND16. */
-double oracle_ppnd16(double p)
-{
-    double q = p - 0.5, r, val;
-    if (fabs(q) <= 0.425) {
-        r = 0.180625 - q * q;
-        double num = fma(fma(fma(fma(fma(fma(fma(r, 2509.0809287301226727, 33430.575583588128105), r, 67265.770927008700853), r,
-                     45921.953931549871457), r, 13731.693765509461125), r, 1971.5909503065514427), r, 133.14166789178437745), r,
-                     3.387132872796366608);
-        double den = fma(fma(fma(fma(fma(fma(fma(r, 5226.495278852545925, 28729.085735721942674), r, 39307.89580009271061), r,
-                     21213.794301586595867), r, 5394.1960214247511077), r, 687.1870074920579083), r, 42.313330701600911252), r, 1.0);
-        return q * num / den;
-    }
-    r = (q < 0) ? p : 1.0 - p;
-    r = sqrt(-oracle_log(r));
-    if (r <= 5.0) {
-        r -= 1.6;
-        double num = fma(fma(fma(fma(fma(fma(fma(r, 7.7454501427834140764e-4, 0.0227238449892691845833), r, 0.24178072517745061177), r,
-                     1.27045825245236838258), r, 3.64784832476320460504), r, 5.7694972214606914055), r, 4.6303378461565452959), r,
-                     1.42343711074968357734);
-        double den = fma(fma(fma(fma(fma(fma(fma(r, 1.05075007164441684324e-9, 5.475938084995344946e-4), r, 0.0151986665636164571966), r,
-                     0.14810397642748007459), r, 0.68976733498510000455), r, 1.6763848301838038494), r, 2.05319162663775882187), r, 1.0);
-        val = num / den;
-    } else {
-        r -= 5.0;
-        double num = fma(fma(fma(fma(fma(fma(fma(r, 2.01033439929228813265e-7, 2.71155556874348757815e-5), r, 0.0012426609473880784386), r,
-                     0.026532189526576123093), r, 0.29656057182850489123), r, 1.7848265399172913358), r, 5.4637849111641143699), r,
-                     6.6579046435011037772);
-        double den = fma(fma(fma(fma(fma(fma(fma(r, 2.04426310338993978564e-15, 1.4215117583164458887e-7), r, 1.8463183175100546818e-5), r,
-                     7.868691311456132591e-4), r, 0.0148753612908506148525), r, 0.13692988092273580531), r, 0.59983220655588793769), r, 1.0);
-        val = num / den;
-    }
-    return (q < 0) ? -val : val;
 }
 
 /* ------------------------------------------------------------------ samplers */
@@ -336,8 +304,55 @@ int oracle_binomial(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t ele
     return binomial_draw(&s, kstep, n, pp);
 }
 
+/* Standard normal by the ziggurat (Marsaglia & Tsang 2000; layer index independent of the value as in Doornik 2005),
+ * 128 layers of equal area with right edges zig_x[0..128] (zig_x[0] the base strip's pseudo-edge, zig_x[1] = R).
+ * Candidate from four Philox words: |u| = the 52 bits (w1 >> 12 : w0) as a fraction, sign = bit 7 of w1, layer = the
+ * low 7 bits of w1; accepted at once when |u| < zig_x[i+1] / zig_x[i] (97 %).  Otherwise the base strip draws from
+ * the tail beyond R (Marsaglia's exponential rejection) and the other layers test the wedge under the density.
+ * Attempt t of a gamma draw takes its first candidate from words 0,1 of block t; every further pair of uniforms or
+ * candidate takes the next block of the sequence NORM_BLOCK0 + (t << 8) + q, q = 0, 1, ... */
+static const double zig_x[129] = SG_ZIG_X, zig_ratio[128] = SG_ZIG_RATIO;
+#define NORM_BLOCK0 0x10000u
+
+static double normal_draw(const ustream *s, uint32_t t, const uint32_t w_first[4])
+{
+    uint32_t w[4] = { w_first[0], w_first[1], w_first[2], w_first[3] };
+    uint32_t q = 0;
+    for (;;) {
+        double mag = u2d(((uint64_t)(0x3ff00000u | (w[1] >> 12)) << 32) | w[0]) - 1.0;
+        int i = (int)(w[1] & 127u), neg = (int)((w[1] >> 7) & 1u);
+        double xi = zig_x[i];
+        if (mag < zig_ratio[i]) { double x = mag * xi; return neg ? -x : x; }
+        if (i == 0) {
+            double xx, yy, u1, u2;
+            do {
+                us_block(s, NORM_BLOCK0 + (t << 8) + q, &u1, &u2); q++;
+                xx = oracle_log(u1) / SG_ZIG_R;
+                yy = oracle_log(u2);
+            } while (-2.0 * yy < xx * xx);
+            return neg ? xx - SG_ZIG_R : SG_ZIG_R - xx;
+        }
+        double x = mag * xi, xi1 = zig_x[i + 1];
+        double f0 = oracle_exp(-0.5 * (xi * xi - x * x)), f1 = oracle_exp(-0.5 * (xi1 * xi1 - x * x));
+        double ua, ub;
+        us_block(s, NORM_BLOCK0 + (t << 8) + q, &ua, &ub); q++;
+        if (f1 + ua * (f0 - f1) < 1.0) return neg ? -x : x;
+        uint32_t ctr[4] = { NORM_BLOCK0 + (t << 8) + q, s->elem, s->stream, s->sweep };
+        oracle_philox(ctr, s->key, w); q++;
+    }
+}
+
+double oracle_normal(uint64_t seed, uint32_t sweep, uint32_t stream, uint32_t elem, uint32_t t)
+{
+    ustream s; us_init(&s, seed, sweep, stream, elem);
+    uint32_t ctr[4] = { t, s.elem, s.stream, s.sweep }, w[4];
+    oracle_philox(ctr, s.key, w);
+    return normal_draw(&s, t, w);
+}
+
 /* Gamma(shape, rate) with the clamps of one_gamma_dist (src/gibbs_2.cpp:39-43);
- * Marsaglia & Tsang, "A simple method for generating gamma variables" (ACM TOMS 26, 2000). */
+ * Marsaglia & Tsang, "A simple method for generating gamma variables" (ACM TOMS 26, 2000).
+ * Attempt t: normal from block t (words 0,1 first, see normal_draw), acceptance uniform u53(words 2,3) of block t. */
 static double gamma_core(const ustream *s, double a, double scale)
 {
     int boost = a < 1.0;
@@ -346,9 +361,10 @@ static double gamma_core(const ustream *s, double a, double scale)
     double c = 1.0 / sqrt(9.0 * d);
     double v = 1.0;
     for (uint32_t t = 0; t < 256; t++) {
-        double u1, u2;
-        us_block(s, t, &u1, &u2);
-        double x = oracle_ppnd16(u1);
+        uint32_t ctr[4] = { t, s->elem, s->stream, s->sweep }, w[4];
+        oracle_philox(ctr, s->key, w);
+        double u2 = oracle_u53(w[2], w[3]);
+        double x = normal_draw(s, t, w);
         v = 1.0 + c * x;
         if (v <= 0.0) continue;
         v = v * v * v;

@@ -23,7 +23,8 @@ HYPER_DEFAULT = dict(ap=0.8005, bp=0.043, ae=2.0506, be=1.325, lp=5.3329, le=1.4
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "gibbs_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    tab = os.path.join(_HERE, "det_tables.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(tab)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
     return so
 
@@ -34,9 +35,11 @@ def lib():
         L = C.CDLL(build())
         d, u32, u64, i32 = C.c_double, C.c_uint32, C.c_uint64, C.c_int
         dp = C.POINTER(C.c_double)
-        for f in ("oracle_log", "oracle_exp", "oracle_lgamma", "oracle_ppnd16"):
+        for f in ("oracle_log", "oracle_exp", "oracle_lgamma"):
             getattr(L, f).restype = d
             getattr(L, f).argtypes = [d]
+        L.oracle_normal.restype = d
+        L.oracle_normal.argtypes = [u64, u32, u32, u32, u32]
         L.oracle_u53.restype = d
         L.oracle_u53.argtypes = [u32, u32]
         L.oracle_binomial.restype = i32

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run ON THE GPU BOX: bench with different batch-width gradings of z_alloc_fused's work list (SIGNER_Z_WIDTHS)
-for w in "99999999:32" "2048:2,512:4,256:8,128:16" "1024:2,256:4,128:8,64:16" "512:2,128:4,64:8,33:16" "512:4,128:8,64:16" "2048:1,1024:2,512:4,256:8,128:16" "256:8,64:16" "1024:8,128:16" "4096:1,2048:2,1024:4,512:8,256:16" ; do
+for w in ${WIDTHS:-"99999999:32" "2048:4" "1024:4" "1024:8" "512:8" "1024:4,512:8" "512:16" "2048:2,1024:4,512:8" "1024:8,512:16" "1024:2,512:4,384:8"} ; do
   SIGNER_Z_WIDTHS=$w python bench.py --no-cpu-baseline --no-e2e --steps ${STEPS:-1000} --warmup 100 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])

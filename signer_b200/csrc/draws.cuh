@@ -1,4 +1,4 @@
-// draws.cuh -- device primitives of the draw specification v4.
+// draws.cuh -- device primitives of the draw specification v6.
 //
 // Everything here is built from IEEE-754 correctly rounded fp64 operations (+ - * / sqrt fma) in
 // a fixed order, plus integer arithmetic, so that results are bit-identical to any other
@@ -11,6 +11,8 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+
+#include "det_tables.h"
 
 namespace sg {
 
@@ -81,7 +83,12 @@ struct UStream {
 };
 
 // ---------------------------------------------------------------- deterministic elementary functions
-// log: fdlibm-style reduction to sqrt(1/2) < m < sqrt(2), degree-7 minimax in s = f/(2+f).
+// log, division-free: x = 2^k z with bits(z) in [OFF, OFF + 2^52) (z in [0.6875, 1.375)); a 128-entry table gives
+// invc ~ 1/z and logc = -log(invc) for the run of bit patterns z falls in; r = fma(z, invc, -1), |r| < 2^-7;
+// log x = k ln2 + logc + log1p(r), log1p by its Taylor polynomial up to r^9, the leading terms summed in two pieces.
+// Table: scripts/make_det_tables.py (det_tables.h; the oracle carries a byte-identical copy).
+__device__ const double g_log_tab[SG_LOG_N][2] = SG_LOG_TABLE;
+
 SG_D double det_log(double x)
 {
     int hx = __double2hiint(x);
@@ -93,21 +100,20 @@ SG_D double det_log(double x)
         k = -54; x = x * 0x1p54; hx = __double2hiint(x); lx = (unsigned)__double2loint(x);
     }
     if (hx >= 0x7ff00000) return x + x;
-    k += (hx >> 20) - 1023;
-    hx &= 0x000fffff;
-    const int i = (hx + 0x95f64) & 0x100000;
-    x = __hiloint2double(hx | (i ^ 0x3ff00000), (int)lx);
-    k += (i >> 20);
-    const double f = x - 1.0;
-    const double s = f / (2.0 + f);
-    const double dk = (double)k;
-    const double z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                              6.666666666666735130e-01);
-    const double R = t2 + t1;
-    const double hfsq = 0.5 * f * f;
-    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+    const int tmp = hx - (int)SG_LOG_OFF_HI;
+    const int i = (tmp >> 13) & (SG_LOG_N - 1);
+    k += tmp >> 20;
+    const double z = __hiloint2double(hx - (tmp & (int)0xfff00000), (int)lx);
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(&g_log_tab[i][0]));    // {invc, logc}
+    const double r = fma(z, t.x, -1.0);
+    const double kd = (double)k;
+    const double w = fma(kd, 6.93147180369123816490e-01, t.y);
+    const double hi = w + r;
+    const double lo = ((w - hi) + r) + kd * 1.90821492927058770002e-10;
+    double q = fma(r, 1.0 / 9.0, -1.0 / 8.0);
+    q = fma(r, q, 1.0 / 7.0); q = fma(r, q, -1.0 / 6.0); q = fma(r, q, 1.0 / 5.0);
+    q = fma(r, q, -1.0 / 4.0); q = fma(r, q, 1.0 / 3.0); q = fma(r, q, -0.5);
+    return (lo + (r * r) * q) + hi;
 }
 
 SG_D double det_exp(double x)
@@ -162,47 +168,6 @@ __device__ __noinline__ double det_lgamma(double x)
     ser = r * ser;
     const double lg = ((y - 0.5) * det_log(y) - y) + 0.91893853320467274178 + ser;
     return lg - corr;
-}
-
-SG_D double horner8(double r, double c7, double c6, double c5, double c4, double c3, double c2, double c1, double c0)
-{
-    double v = fma(r, c7, c6);
-    v = fma(v, r, c5); v = fma(v, r, c4); v = fma(v, r, c3);
-    v = fma(v, r, c2); v = fma(v, r, c1); v = fma(v, r, c0);
-    return v;
-}
-
-// Standard normal quantile, Wichura AS 241 PPND16.
-SG_D double det_ppnd16(double p)
-{
-    const double q = p - 0.5;
-    if (fabs(q) <= 0.425) {
-        const double r = 0.180625 - q * q;
-        const double num = horner8(r, 2509.0809287301226727, 33430.575583588128105, 67265.770927008700853, 45921.953931549871457,
-                                   13731.693765509461125, 1971.5909503065514427, 133.14166789178437745, 3.387132872796366608);
-        const double den = horner8(r, 5226.495278852545925, 28729.085735721942674, 39307.89580009271061, 21213.794301586595867,
-                                   5394.1960214247511077, 687.1870074920579083, 42.313330701600911252, 1.0);
-        return q * num / den;
-    }
-    double r = (q < 0) ? p : 1.0 - p;
-    r = sqrt(-det_log(r));
-    double val;
-    if (r <= 5.0) {
-        r -= 1.6;
-        const double num = horner8(r, 7.7454501427834140764e-4, 0.0227238449892691845833, 0.24178072517745061177, 1.27045825245236838258,
-                                   3.64784832476320460504, 5.7694972214606914055, 4.6303378461565452959, 1.42343711074968357734);
-        const double den = horner8(r, 1.05075007164441684324e-9, 5.475938084995344946e-4, 0.0151986665636164571966, 0.14810397642748007459,
-                                   0.68976733498510000455, 1.6763848301838038494, 2.05319162663775882187, 1.0);
-        val = num / den;
-    } else {
-        r -= 5.0;
-        const double num = horner8(r, 2.01033439929228813265e-7, 2.71155556874348757815e-5, 0.0012426609473880784386, 0.026532189526576123093,
-                                   0.29656057182850489123, 1.7848265399172913358, 5.4637849111641143699, 6.6579046435011037772);
-        const double den = horner8(r, 2.04426310338993978564e-15, 1.4215117583164458887e-7, 1.8463183175100546818e-5, 7.868691311456132591e-4,
-                                   0.0148753612908506148525, 0.13692988092273580531, 0.59983220655588793769, 1.0);
-        val = num / den;
-    }
-    return (q < 0) ? -val : val;
 }
 
 // ---------------------------------------------------------------- binomial
@@ -296,8 +261,59 @@ SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double
     return flip ? n - x : x;
 }
 
+// ---------------------------------------------------------------- normal (ziggurat)
+// Marsaglia & Tsang 2000 with the layer index independent of the value (Doornik 2005): 128 layers of equal area with
+// right edges g_zig_x[0..128].  Candidate from four Philox words: |u| = the 52 bits (w1 >> 12 : w0) as a fraction,
+// sign = bit 7 of w1, layer = the low 7 bits of w1; accepted at once when |u| < x[i+1]/x[i] (97 %).  Otherwise the
+// base strip draws from the tail beyond R and the other layers test the wedge under the density.  Attempt t of a gamma
+// draw takes its first candidate from block t; further uniforms / candidates take blocks kNormBlock0 + (t << 8) + q.
+__device__ const double g_zig_x[129] = SG_ZIG_X;
+__device__ const double g_zig_ratio[128] = SG_ZIG_RATIO;
+constexpr uint32_t kNormBlock0 = 0x10000u;
+
+__device__ __noinline__ double normal_slow(const UStream &s, uint32_t t, U4 w)
+{
+    uint32_t q = 0;
+    for (;;) {
+        const double mag = __hiloint2double((int)(0x3ff00000u | (w.y >> 12)), (int)w.x) - 1.0;
+        const int i = (int)(w.y & 127u);
+        const bool neg = (w.y >> 7) & 1u;
+        const double xi = __ldg(&g_zig_x[i]);
+        if (mag < __ldg(&g_zig_ratio[i])) { const double x = mag * xi; return neg ? -x : x; }
+        if (i == 0) {
+            double xx, yy;
+            do {
+                double u1, u2;
+                s.pair(kNormBlock0 + (t << 8) + q, u1, u2); ++q;
+                xx = det_log(u1) / SG_ZIG_R;
+                yy = det_log(u2);
+            } while (-2.0 * yy < xx * xx);
+            return neg ? xx - SG_ZIG_R : SG_ZIG_R - xx;
+        }
+        const double x = mag * xi, xi1 = __ldg(&g_zig_x[i + 1]);
+        const double f0 = det_exp(-0.5 * (xi * xi - x * x)), f1 = det_exp(-0.5 * (xi1 * xi1 - x * x));
+        double ua, ub;
+        s.pair(kNormBlock0 + (t << 8) + q, ua, ub); ++q;
+        if (f1 + ua * (f0 - f1) < 1.0) return neg ? -x : x;
+        w = s.words(kNormBlock0 + (t << 8) + q); ++q;
+    }
+}
+
+// w: the four words of block t
+SG_D double normal_draw(const UStream &s, uint32_t t, const U4 &w)
+{
+    const double mag = __hiloint2double((int)(0x3ff00000u | (w.y >> 12)), (int)w.x) - 1.0;
+    const int i = (int)(w.y & 127u);
+    if (mag < __ldg(&g_zig_ratio[i])) {
+        const double x = mag * __ldg(&g_zig_x[i]);
+        return ((w.y >> 7) & 1u) ? -x : x;
+    }
+    return normal_slow(s, t, w);
+}
+
 // ---------------------------------------------------------------- gamma (Marsaglia & Tsang 2000)
-// Gamma(shape, rate) with one_gamma_dist's clamps (src/gibbs_2.cpp:39-43).  Attempt t reads block t.
+// Gamma(shape, rate) with one_gamma_dist's clamps (src/gibbs_2.cpp:39-43).  Attempt t reads block t: the normal
+// from words 0,1 (normal_draw), the acceptance uniform from words 2,3.
 __device__ __noinline__ double gamma_draw(const UStream &s, double shape, double rate)
 {
     const double a = (kTiny < shape) ? shape : kTiny;
@@ -309,9 +325,9 @@ __device__ __noinline__ double gamma_draw(const UStream &s, double shape, double
     const double c = 1.0 / sqrt(9.0 * d);
     double v = 1.0;
     for (uint32_t t = 0; t < 256; ++t) {
-        double u1, u2;
-        s.pair(t, u1, u2);
-        const double x = det_ppnd16(u1);
+        const U4 w = s.words(t);
+        const double u2 = u53(w.z, w.w);
+        const double x = normal_draw(s, t, w);
         v = 1.0 + c * x;
         if (v <= 0.0) continue;
         v = v * v * v;

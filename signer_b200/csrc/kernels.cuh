@@ -49,13 +49,8 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 // flushed once per block) and sum_i Z straight to L2 integer atomics.  Batches are claimed
 // heaviest-first from a global counter, one ahead of the batch being processed.
 // ------------------------------------------------------------------------------------------------
-#ifndef SG_ZWARPS
-#define SG_ZWARPS 8
-#endif
-#ifndef SG_ZBLOCKS
-#define SG_ZBLOCKS 3
-#endif
-constexpr int kZWarps = SG_ZWARPS;   // warps per block (they share only the block's Zin accumulator)
+constexpr int kZMaxWarps = 24;   // most warps per block; the host picks the block size per K (z_pick_block) -- the warps of a
+                                 // block share only its Zin accumulator
 constexpr int kZChunk = 1;        // batches of 32 cells per claim
 constexpr int kNDirect = 32;      // largest count drawn by the direct method
 constexpr int kZinSmemMax = 40 * 1024;
@@ -205,7 +200,7 @@ __device__ unsigned g_z_batch_cycles[1 << 16];
 
 SG_D int z_expo(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
-__global__ void __launch_bounds__(32 * kZWarps, SG_ZBLOCKS) z_alloc_fused(const ZParams p)
+__global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -215,7 +210,7 @@ __global__ void __launch_bounds__(32 * kZWarps, SG_ZBLOCKS) z_alloc_fused(const 
     const int ng = z_groups(K), R = 4 * ng;                             // groups of four thresholds, rows of buf
     unsigned char *ord = base + (size_t)8 * R * 32 + lane;              // ord[t * 32]: class visited at step t
     unsigned *zc = reinterpret_cast<unsigned *>(base + (size_t)8 * R * 32 + ((size_t)K * 32 + 7) / 8 * 8) + lane;   // zc[w * 32]: counts of classes 4w..4w+3
-    int *zin_s = p.zin_smem ? reinterpret_cast<int *>(smem_raw + (size_t)kZWarps * p.warp_smem) : nullptr;
+    int *zin_s = p.zin_smem ? reinterpret_cast<int *>(smem_raw + (size_t)(blockDim.x >> 5) * p.warp_smem) : nullptr;
     const int nw = (K + 3) / 4;
 
     // zero the other half of the ping-pong for the next launch
@@ -225,7 +220,7 @@ __global__ void __launch_bounds__(32 * kZWarps, SG_ZBLOCKS) z_alloc_fused(const 
         for (size_t i = gtid; i < (size_t)K * J; i += gsz) p.Znj_next[i] = 0;
     }
     if (zin_s) {
-        for (int i = tid; i < I * K; i += 32 * kZWarps) zin_s[i] = 0;
+        for (int i = tid; i < I * K; i += blockDim.x) zin_s[i] = 0;
         __syncthreads();
     }
     for (int w = 0; w < nw; ++w) zc[w * 32] = 0;            // invariant: all zero between cells
@@ -407,7 +402,7 @@ __global__ void __launch_bounds__(32 * kZWarps, SG_ZBLOCKS) z_alloc_fused(const 
     }
     if (zin_s) {
         __syncthreads();
-        for (int i = tid; i < I * K; i += 32 * kZWarps) {
+        for (int i = tid; i < I * K; i += blockDim.x) {
             const int v = zin_s[i];
             if (v) atomicAdd(p.Zin + i, v);
         }
@@ -905,7 +900,13 @@ __global__ void test_math(int fn, const double *x, double *y, int n)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    y[i] = fn == 0 ? det_log(v) : fn == 1 ? det_exp(v) : fn == 2 ? det_lgamma(v) : det_ppnd16(v);
+    if (fn == 3) {                                       // ziggurat normal of element i, attempt (uint32) x[i], seed 12345
+        UStream us; us.init(Key{12345u, 0u}, 0u, 3u, (uint32_t)i);
+        const uint32_t t = (uint32_t)v;
+        y[i] = normal_draw(us, t, us.words(t));
+        return;
+    }
+    y[i] = fn == 0 ? det_log(v) : fn == 1 ? det_exp(v) : det_lgamma(v);
 }
 __global__ void test_binomial(Key key, uint32_t sweep, uint32_t stream, int kstep, const int *n, const double *pp, int *out, int count)
 {

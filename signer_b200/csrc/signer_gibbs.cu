@@ -70,6 +70,8 @@ struct DeviceData {
 
 // cells per batch of z_alloc_fused's work list for cells of count n (see upload_data); SIGNER_Z_WIDTHS="n:w,n:w,..."
 // (descending n) overrides the built-in grading for experiments
+const bool g_sort_rounds = [] { const char *e = std::getenv("SIGNER_Z_SORT_EXACT"); return !(e && e[0] == '1'); }();
+
 int batch_width(int n)
 {
     static const std::vector<std::pair<int, int>> grade = [] {
@@ -130,7 +132,11 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
         }
         std::vector<size_t> idx(nz);
         for (size_t t = 0; t < nz; ++t) idx[t] = t;
-        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cnt[a] > cnt[b]; });
+        // sort key: counts above kNDirect by value; smaller ones by their number of direct-method rounds (four
+        // draws per Philox block), so that cells that cost the same stay in genome-major order and a warp's lanes
+        // read few distinct columns of E
+        auto key = [&](size_t t) { return cnt[t] > kNDirect ? cnt[t] : (g_sort_rounds ? 4 * ((cnt[t] + 3) / 4) : cnt[t]); };
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return key(a) > key(b); });
         crow.reserve(nz + 4096); ccol.reserve(nz + 4096); cn.reserve(nz + 4096);
         size_t t = 0;
         while (t < nz) {
@@ -226,7 +232,7 @@ struct signer_chain {
     double *acache_p = nullptr, *acache_e = nullptr;   // [3][I*K], [3][K*J]: A-only terms of the MH ratios (kernels.cuh, ACache)
     unsigned long long *tile_counter = nullptr;
     unsigned long long z_launches = 0;
-    int z_grid = 0, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
+    int z_grid = 0, z_warps = 8, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
     int ksplit = 1;
     Hyper h{};
     Key key{};
@@ -308,14 +314,14 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     p.Zin_next = c->Zin[c->zcur]; p.Znj_next = c->Znj[c->zcur];
     p.Zcube = zcube;
     p.counter = c->tile_counter;
-    p.base = c->z_launches * (unsigned long long)(c->n_chunks + c->z_grid * kZWarps);   // every warp overshoots once
+    p.base = c->z_launches * (unsigned long long)(c->n_chunks + c->z_grid * c->z_warps);   // every warp overshoots once
     p.warp_smem = c->z_warp_smem; p.zin_smem = c->z_zin_smem;
     p.draw_count = c->draw_count;
     p.key = c->key; p.sweep = sweep; p.stream = stream_id;
     if (zcube) CU(cudaMemsetAsync(zcube, 0, sizeof(double) * (size_t)c->I * c->J * c->K, c->stream));
     {
         ProfScope ps(c, 0);
-        z_alloc_fused<<<c->z_grid, 32 * kZWarps, (size_t)c->z_warp_smem * kZWarps + (c->z_zin_smem ? c->nP * sizeof(int) : 0), c->stream>>>(p);
+        z_alloc_fused<<<c->z_grid, 32 * c->z_warps, (size_t)c->z_warp_smem * c->z_warps + (c->z_zin_smem ? c->nP * sizeof(int) : 0), c->stream>>>(p);
     }
     CU(cudaGetLastError());
     c->z_launches++;
@@ -600,14 +606,27 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->n_chunks = (c->n_batches + kZChunk - 1) / kZChunk;
     c->z_warp_smem = (int)z_smem_bytes_per_warp(K);
     c->z_zin_smem = (c->nP * sizeof(int) <= (size_t)kZinSmemMax) ? 1 : 0;
-    const size_t zsm = (size_t)c->z_warp_smem * kZWarps + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
     ST(ensure_device_setup(c->device));
-    if (zsm > (size_t)g_z_dyn_smem_max[c->device]) return fail(SIGNER_ERR_ARG, "z_alloc_fused: K too large for shared memory");
-    int occ = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * kZWarps, zsm));
+    // block size: the configuration that keeps the most warps resident per SM (at most kZMaxWarps: the register
+    // file holds that many at the kernel's 80 registers); ties go to fewer, larger blocks (fewer Zin accumulators
+    // in shared memory, which leaves more of the SM's 256 KB to L1)
+    int sms = 0, best_w = 0, best_b = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    if (occ < 1) return fail(SIGNER_ERR_ARG, "z_alloc_fused does not fit on an SM for this K");
-    c->z_grid = std::max(1, std::min((c->n_chunks + kZWarps - 1) / kZWarps, occ * sms));
+    for (int w : {24, 12, 8, 6, 4, 3, 2, 1}) {
+        const size_t zsm = (size_t)c->z_warp_smem * w + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
+        if (zsm > (size_t)g_z_dyn_smem_max[c->device]) continue;
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * w, zsm));
+        occ = std::min(occ, kZMaxWarps / w);
+        if (occ * w > best_w * best_b) { best_w = w; best_b = occ; }
+    }
+    if (best_w == 0) return fail(SIGNER_ERR_ARG, "z_alloc_fused: K too large for shared memory");
+    if (const char *e = std::getenv("SIGNER_Z_BLOCK")) {          // experiments: "warps:blocks_per_sm"
+        int w = 0, b = 0;
+        if (std::sscanf(e, "%d:%d", &w, &b) == 2 && w >= 1 && w <= kZMaxWarps && b >= 1) { best_w = w; best_b = b; }
+    }
+    c->z_warps = best_w;
+    c->z_grid = std::max(1, std::min((c->n_chunks + best_w - 1) / best_w, best_b * sms));
     c->ksplit = (K + kEGroup - 1) / kEGroup;
 
     // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device

@@ -38,11 +38,20 @@ def test_deterministic_math_accuracy(oracle):
     x = np.concatenate([10 ** rng.uniform(-300, 300, 3000), rng.uniform(0, 30, 3000)])
     got = np.array([L.oracle_lgamma(v) for v in x]); ref = special.gammaln(x)
     assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 2e-14
-    p = np.concatenate([rng.uniform(0, 1, 4000), 10 ** rng.uniform(-300, -2, 2000)]); p = p[(p > 0) & (p < 1)]
-    got = np.array([L.oracle_ppnd16(v) for v in p]); ref = stats.norm.ppf(p)
-    assert np.max(np.abs(got - ref) / np.maximum(1e-3, np.abs(ref))) < 1e-13
     assert L.oracle_log(0.0) == -math.inf and math.isnan(L.oracle_log(-1.0)) and L.oracle_exp(-800.0) == 0.0
     assert L.oracle_exp(800.0) == math.inf and L.oracle_lgamma(0.0) == math.inf
+
+
+def test_normal_law(oracle):
+    """ziggurat normal: KS against the normal cdf, moments, and the mass beyond a few thresholds (layers, wedges, tail)"""
+    L = oracle.lib()
+    z = np.array([L.oracle_normal(7, 1, 3, e, e & 3) for e in range(200000)])
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 4 * np.sqrt(2 / z.size)
+    for thr in (0.5, 1.0, 2.0, 3.0, 3.442619855899):
+        pr = 2 * stats.norm.sf(thr)
+        assert abs((np.abs(z) > thr).mean() - pr) < 4.5 * np.sqrt(pr * (1 - pr) / z.size), thr
+    assert abs((z > 0).mean() - 0.5) < 4 / np.sqrt(z.size)
 
 
 @pytest.mark.parametrize("n,p", [(1, 0.3), (20, 0.1), (50, 0.59), (120, 0.2), (200, 0.4), (1000, 0.02), (1000, 0.031),
@@ -98,6 +107,30 @@ def test_multinomial_cell_laws_and_invariants(oracle):
     assert oracle.multinomial_cell(3, 0, 1, 0, 0, 9, np.array([[2.0]]), np.array([[3.0]]))[0] == 9
     z = oracle.multinomial_cell(3, 0, 1, 0, 0, 9, np.zeros((1, 3)), np.ones((3, 1)))
     assert list(z) == [0, 0, 9]
+
+
+def test_multinomial_chain_joint_law(oracle):
+    """large counts (bucket-ordered chain + direct draws for the remainder): every class marginal and every pair sum
+    is binomial -- which pins the joint law well beyond the means"""
+    rng = np.random.default_rng(3)
+    K = 9
+    P = rng.gamma(0.3, 1.0, size=(1, K)); P[0, 4] = 0.0
+    E = rng.gamma(1.0, 1.0, size=(K, 1))
+    q = P[0] * E[:, 0]; q = q / q.sum()
+    for n in (40, 150, 3000):
+        N = 3000
+        Z = np.array([oracle.multinomial_cell(11, sw, 1, 0, 0, n, P, E) for sw in range(N)])
+        assert (Z.sum(axis=1) == n).all() and (Z[:, 4] == 0).all()
+        for a in range(K):
+            for b in range(a, K):
+                pr = q[a] if a == b else q[a] + q[b]
+                if pr <= 0 or pr >= 1:
+                    continue
+                x = Z[:, a] if a == b else Z[:, a] + Z[:, b]
+                zs = (x.mean() - n * pr) / np.sqrt(n * pr * (1 - pr) / N)
+                assert abs(zs) < 4.5, (n, a, b, zs)
+                vr = x.var() / (n * pr * (1 - pr))
+                assert abs(vr - 1) < 5 * np.sqrt((2 + 1 / (n * pr * (1 - pr))) / N) + 0.01, (n, a, b, vr)   # var of s^2 incl. kurtosis
 
 
 def test_perm_is_uniform(oracle):
