@@ -142,21 +142,23 @@ SG_D double det_exp(double x)
     return __longlong_as_double(__double_as_longlong(y) + ((long long)(k + 1000) << 52)) * 0x1p-1000;
 }
 
-// lgamma for x > 0: recurrence up to y >= 8, then 8 Stirling terms.
-__device__ __noinline__ double det_lgamma(double x)
+// lgamma for x > 0: recurrence up to y >= 8, then 8 Stirling terms.  Written without a data-dependent branch (the
+// recurrence runs on a dummy argument when x >= 8 and its logarithm is discarded) so that several evaluations inline
+// into one straight-line block and overlap; the selected operations and their order are the specification's.
+SG_D double det_lgamma(double x)
 {
     if (x != x) return x;
     if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
     if (x == 0.0 || x > 1.7e308) return __longlong_as_double(0x7ff0000000000000LL);
-    double y = x, corr = 0.0;
-    if (x < 8.0) {
-        double prod = x;
-        prod = prod * (x + 1.0); prod = prod * (x + 2.0); prod = prod * (x + 3.0);
-        prod = prod * (x + 4.0); prod = prod * (x + 5.0); prod = prod * (x + 6.0);
-        prod = prod * (x + 7.0);
-        corr = det_log(prod);
-        y = x + 8.0;
-    }
+    const bool small = x < 8.0;
+    const double xs = small ? x : 1.0;
+    double prod = xs;
+    prod = prod * (xs + 1.0); prod = prod * (xs + 2.0); prod = prod * (xs + 3.0);
+    prod = prod * (xs + 4.0); prod = prod * (xs + 5.0); prod = prod * (xs + 6.0);
+    prod = prod * (xs + 7.0);
+    const double lp = det_log(prod);
+    const double corr = small ? lp : 0.0;
+    const double y = small ? x + 8.0 : x;
     const double r = 1.0 / y, r2 = r * r;
     double ser = fma(r2, -2.9550653594771242e-02, 6.4102564102564100e-03);
     ser = fma(r2, ser, -1.9175269175269176e-03);

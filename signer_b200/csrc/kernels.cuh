@@ -22,6 +22,7 @@
 namespace sg {
 
 constexpr unsigned kFull = 0xffffffffu;
+
 constexpr int kEThreads = 256;    // e_family: 128 genomes x 2 class pairs
 constexpr int kLLChunk = 32;      // rows per log-likelihood chunk
 
@@ -213,12 +214,6 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
     int *zin_s = p.zin_smem ? reinterpret_cast<int *>(smem_raw + (size_t)(blockDim.x >> 5) * p.warp_smem) : nullptr;
     const int nw = (K + 3) / 4;
 
-    // zero the other half of the ping-pong for the next launch
-    {
-        const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gsz = (size_t)gridDim.x * blockDim.x;
-        for (size_t i = gtid; i < (size_t)I * K; i += gsz) p.Zin_next[i] = 0;
-        for (size_t i = gtid; i < (size_t)K * J; i += gsz) p.Znj_next[i] = 0;
-    }
     if (zin_s) {
         for (int i = tid; i < I * K; i += blockDim.x) zin_s[i] = 0;
         __syncthreads();
@@ -234,6 +229,12 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
     int cur = 0, pend = 0;
     if (lane == 0) cur = (int)(atomicAdd(p.counter, 1ULL) - p.base);
     cur = __shfl_sync(kFull, cur, 0);
+    // zero the other half of the ping-pong for the next launch
+    {
+        const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gsz = (size_t)gridDim.x * blockDim.x;
+        for (size_t i = gtid; i < (size_t)I * K; i += gsz) p.Zin_next[i] = 0;
+        for (size_t i = gtid; i < (size_t)K * J; i += gsz) p.Znj_next[i] = 0;
+    }
     while (cur < p.n_batches) {
 #ifdef SG_Z_TIMING
         const long long t_begin = clock64();
@@ -413,6 +414,8 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
 // element-wise updates shared by the two families
 // ------------------------------------------------------------------------------------------------
 // steps 4/5 (src/gibbs_2.cpp:140-169)
+SG_D void sg_prefetch(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double a, double b)
 {
     UStream us; us.init(key, sweep, stream, e);
@@ -427,9 +430,12 @@ SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, doubl
 // in a per-element cache: A changes only when a proposal is accepted, and then its terms are exactly the
 // y-terms just evaluated.  Same operations on the same operands, so the result is bit-identical to
 // re-evaluating them (which is what the oracle does).
-struct ACache { double *lg1, *lg2, *lg; };     // lgamma(A+1), lgamma(A*A/var), log(A)
+struct ACache { double *lg1, *lg2, *lg; };
+#ifndef SG_UPDATE_A_INLINE
+#define SG_UPDATE_A_INLINE SG_D
+#endif     // lgamma(A+1), lgamma(A*A/var), log(A)
 
-__device__ __noinline__ double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var,
+SG_UPDATE_A_INLINE double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var,
                                         const ACache c, size_t ci)
 {
     UStream us; us.init(key, sweep, stream, e);
@@ -489,12 +495,21 @@ struct PParams {
     Ops ops;
 };
 
+#ifdef SG_Z_TIMING      // experiments only: clocks of thread 0 of each block of the last p_family launch
+__device__ long long g_p_clock[64][8];
+#define SG_PCLK(slot) if (threadIdx.x == 0 && blockIdx.x < 64) g_p_clock[blockIdx.x][slot] = clock64();
+#else
+#define SG_PCLK(slot)
+#endif
+
 __global__ void __launch_bounds__(128) p_family(const PParams p)
 {
+    SG_PCLK(0)
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.IK) return;
     double P = p.P[e], Ap = p.Ap[e], Bp = p.Bp[e];
     for (int o = 0; o < p.ops.n; ++o) {
+        SG_PCLK(1 + 2 * o)
         const int op = p.ops.get(o);
         if (op == 2) {
             double tot = 0.0;
@@ -517,6 +532,7 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
                 }
                 tot = tot + part;
             }
+            SG_PCLK(2 + 2 * o)
             UStream us; us.init(p.key, p.sweep, kStP, (uint32_t)e);
             const double shape = Ap + 1 + (double)p.Zin[e];
             const double rate = Bp + tot;
@@ -527,6 +543,7 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
             Ap = update_a(p.key, p.sweep, kStAp, (uint32_t)e, Ap, P, Bp, p.h.lp, p.h.var_ap, p.acache, (size_t)e);
         }
     }
+    SG_PCLK(7)
     p.P[e] = P; p.Ap[e] = Ap; p.Bp[e] = Bp;
     if (p.Ps_slot) p.Ps_slot[e] = P;
     if (p.Aps_slot) p.Aps_slot[e] = Ap;
@@ -582,9 +599,17 @@ __device__ __noinline__ void e_update_element(const EParams &p, size_t e, double
     Eo = E;
 }
 
+#ifdef SG_Z_TIMING      // experiments only: per-block phase clocks of the last e_family launch
+__device__ long long g_e_clock[4096][5];
+#define SG_ECLK(slot) if (threadIdx.x == 0 && blockIdx.x + gridDim.x * blockIdx.y < 4096) g_e_clock[blockIdx.x + gridDim.x * blockIdx.y][slot] = clock64();
+#else
+#define SG_ECLK(slot)
+#endif
+
 __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
 {
-    __shared__ double E_s[kSeg * kEGroup];                // [128][4]
+    SG_ECLK(0)
+    __shared__ __align__(32) double E_s[kSeg * kEGroup];  // [128][4]; classes beyond K and genomes beyond J stay zero
     const int tid = threadIdx.x, jl = tid & (kSeg - 1), h = tid >> 7;
     const int I = p.I, J = p.J, K = p.K;
     const int seg = blockIdx.x, j0 = seg * kSeg, j = j0 + jl;
@@ -593,20 +618,29 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
     const int ka = kBegin + 2 * h, kb = ka + 1;           // this thread's two classes
     bool has3 = false;
     for (int o = 0; o < p.ops.n; ++o) has3 |= (p.ops.get(o) == 3);
+    E_s[tid] = 0.0; E_s[tid + kEThreads] = 0.0;           // kSeg * kEGroup == 2 * kEThreads
+    __syncthreads();
 
     if (j < J && ka < kEnd) {
+        // the element state is wanted only after the P'W chain: start bringing it in now
+        {
+            const size_t e = (size_t)ka + (size_t)K * j;
+            sg_prefetch(p.E + e); sg_prefetch(p.Ae + e); sg_prefetch(p.Be + e); sg_prefetch(p.Znj + e);
+            sg_prefetch(p.acache.lg1 + e); sg_prefetch(p.acache.lg2 + e); sg_prefetch(p.acache.lg + e);
+        }
         double acc0 = 0.0, acc1 = 0.0;
         if (has3) {
             const double *Wc = p.W + j;
             const double *P0 = p.P + (size_t)I * ka;
             const double *P1 = p.P + (size_t)I * min(kb, K - 1);
-#pragma unroll 8
+#pragma unroll 16
             for (int i = 0; i < I; ++i) {
                 const double w = Wc[(size_t)i * p.Jp];
                 acc0 = fma(__ldg(P0 + i), w, acc0);
                 acc1 = fma(__ldg(P1 + i), w, acc1);
             }
         }
+        SG_ECLK(1)
         double Eo;
         e_update_element(p, (size_t)ka + (size_t)K * j, acc0, Eo);
         E_s[jl * kEGroup + (ka - kBegin)] = Eo;
@@ -615,28 +649,42 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
             E_s[jl * kEGroup + (kb - kBegin)] = Eo;
         }
     }
+    SG_ECLK(2)
     if (!p.do_corrE) return;
     __syncthreads();
+    SG_ECLK(3)
+    // W E' of this segment: one thread per context row, the row of W read once (32 genomes in flight) for the block's
+    // four classes -- four independent fma chains, each in ascending genome order
     const int jn = min(kSeg, J - j0);
     const int Kn = kEnd - kBegin;
-    for (int o = tid; o < I * Kn; o += kEThreads) {
-        const int i = o / Kn, kk = o - i * Kn;
+    const double4 *E4 = reinterpret_cast<const double4 *>(E_s);
+    for (int i = tid; i < I; i += kEThreads) {
         const double *Wr = p.W + (size_t)i * p.Jp + j0;    // 16-byte aligned: Jp and j0 are multiples of 32
-        double acc = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int c = 0;
-        for (; c + 16 <= jn; c += 16) {
-            double2 w[8];
+        for (; c + 32 <= jn; c += 32) {
+            double2 w[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const double2 *>(Wr + c + 2 * u);
+            for (int u = 0; u < 16; ++u) w[u] = *reinterpret_cast<const double2 *>(Wr + c + 2 * u);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                acc = fma(w[u].x, E_s[(c + 2 * u) * kEGroup + kk], acc);
-                acc = fma(w[u].y, E_s[(c + 2 * u + 1) * kEGroup + kk], acc);
+            for (int u = 0; u < 16; ++u) {
+                const double4 e0 = E4[c + 2 * u], e1 = E4[c + 2 * u + 1];
+                a0 = fma(w[u].x, e0.x, a0); a1 = fma(w[u].x, e0.y, a1); a2 = fma(w[u].x, e0.z, a2); a3 = fma(w[u].x, e0.w, a3);
+                a0 = fma(w[u].y, e1.x, a0); a1 = fma(w[u].y, e1.y, a1); a2 = fma(w[u].y, e1.z, a2); a3 = fma(w[u].y, e1.w, a3);
             }
         }
-        for (; c < jn; ++c) acc = fma(Wr[c], E_s[c * kEGroup + kk], acc);
-        p.corrE_part[(size_t)seg * ((size_t)I * K) + (size_t)i + (size_t)I * (kBegin + kk)] = acc;
+        for (; c < jn; ++c) {
+            const double wv = Wr[c];
+            const double4 e0 = E4[c];
+            a0 = fma(wv, e0.x, a0); a1 = fma(wv, e0.y, a1); a2 = fma(wv, e0.z, a2); a3 = fma(wv, e0.w, a3);
+        }
+        double *dst = p.corrE_part + (size_t)seg * ((size_t)I * K) + (size_t)i + (size_t)I * kBegin;
+        dst[0] = a0;
+        if (Kn > 1) dst[(size_t)I] = a1;
+        if (Kn > 2) dst[(size_t)I * 2] = a2;
+        if (Kn > 3) dst[(size_t)I * 3] = a3;
     }
+    SG_ECLK(4)
 }
 
 // ------------------------------------------------------------------------------------------------

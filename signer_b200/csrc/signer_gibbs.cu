@@ -629,6 +629,7 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->z_grid = std::max(1, std::min((c->n_chunks + best_w - 1) / best_w, best_b * sms));
     c->ksplit = (K + kEGroup - 1) / kEGroup;
 
+
     // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device
     if (deferred_init) {                                  // a column shard: its peers take part (sharded_run)
         CU(cudaStreamSynchronize(c->stream));
@@ -1385,6 +1386,14 @@ void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 } // extern "C"
 
 #ifdef SG_Z_TIMING
+extern "C" int signer_debug_e_clocks(long long *out, int nblocks)
+{
+    return (int)cudaMemcpyFromSymbol(out, sg::g_e_clock, sizeof(long long) * 5 * (size_t)nblocks);
+}
+extern "C" int signer_debug_p_clocks(long long *out, int nblocks)
+{
+    return (int)cudaMemcpyFromSymbol(out, sg::g_p_clock, sizeof(long long) * 8 * (size_t)nblocks);
+}
 extern "C" int signer_debug_batch_cycles(unsigned *out, int n)
 {
     return (int)cudaMemcpyFromSymbol(out, sg::g_z_batch_cycles, sizeof(unsigned) * (size_t)n);
