@@ -30,3 +30,11 @@ for lo, hi in [(0, 10), (10, 100), (100, 300), (300, 1000), (1000, 2000), (2000,
     hi = min(hi, n)
     if lo >= hi: break
     print("batches %6d..%6d  n %6d..%6d  mean cycles %9.0f  max %9d" % (lo, hi, cnt[min(lo * 32, cnt.size - 1)], cnt[min(hi * 32 - 1, cnt.size - 1)], out[lo:hi].mean(), out[lo:hi].max()))
+
+ph = np.zeros((2, 8), dtype=np.uint64)
+L.signer_debug_z_phases.argtypes = [C.c_void_p]
+assert L.signer_debug_z_phases(ph.ctypes.data_as(C.c_void_p)) == 0
+names = ["cells+claim", "staging", "direct loop", "sort", "chain", "tail", "flush+emit", "-"]
+tot = ph.sum()
+for c, cname in enumerate(["small batches", "large batches"]):
+    print(cname, " ".join("%s %.1f%%" % (names[i], 100.0 * ph[c, i] / tot) for i in range(7)), " | class total %.1f%%" % (100.0 * ph[c].sum() / tot))

@@ -138,8 +138,11 @@ SG_D void z_count(unsigned *zc, int cls) { atomicAdd(zc + (cls >> 2) * 32, 1u <<
 
 // the direct method for one batch: lane draws nn (0 for lanes that take no part) classes, four per Philox block;
 // draw t uses word t&3 of block t>>2 of the lane's stream.  The group ends stay in registers for the whole cell.
+// Every draw is added to the statistics at once (measured faster than counting per class and flushing: the flush
+// walks all K classes with few lanes busy).
 template <int NG>
-SG_D void z_direct(const double *buf, unsigned *zc, const UStream &us, int ng, int nn, int tmax, double Sd)
+SG_D void z_direct(const double *buf, const UStream &us, int ng, int nn, int tmax, double Sd,
+                   const ZParams &p, int *zin_s, int row, int col)
 {
     double ge[NG > 0 ? NG : 1];
     if (NG > 0) {
@@ -150,10 +153,10 @@ SG_D void z_direct(const double *buf, unsigned *zc, const UStream &us, int ng, i
         const U4 w4 = us.words((uint32_t)t0 >> 2);                              // converged: once per four draws
         int c0, c1, c2, c3;
         z_search4<NG>(buf, ng, NG > 0 ? ge : nullptr, u32(w4.x) * Sd, u32(w4.y) * Sd, u32(w4.z) * Sd, u32(w4.w) * Sd, c0, c1, c2, c3);
-        if (t0 < nn) z_count(zc, c0);
-        if (t0 + 1 < nn) z_count(zc, c1);
-        if (t0 + 2 < nn) z_count(zc, c2);
-        if (t0 + 3 < nn) z_count(zc, c3);
+        if (t0 < nn) z_emit(p, zin_s, row, col, c0, 1);
+        if (t0 + 1 < nn) z_emit(p, zin_s, row, col, c1, 1);
+        if (t0 + 2 < nn) z_emit(p, zin_s, row, col, c2, 1);
+        if (t0 + 3 < nn) z_emit(p, zin_s, row, col, c3, 1);
     }
 }
 
@@ -197,6 +200,10 @@ SG_D void z_tail(const double *buf, unsigned *zc, const ZParams &p, int lane, in
 
 #ifdef SG_Z_TIMING      // experiments only: cycles each batch of the last launch took (its warp's wall clock)
 __device__ unsigned g_z_batch_cycles[1 << 16];
+__device__ unsigned long long g_z_phase[2][8];      // [small/large][phase] warp-cycles summed over batches (all launches)
+#define SG_ZCLK(ph) { const long long t_now = clock64(); if (lane == 0) atomicAdd(&g_z_phase[t_large][ph], (unsigned long long)(t_now - t_last)); t_last = t_now; }
+#else
+#define SG_ZCLK(ph)
 #endif
 
 SG_D int z_expo(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
@@ -229,6 +236,11 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
     int cur = 0, pend = 0;
     if (lane == 0) cur = (int)(atomicAdd(p.counter, 1ULL) - p.base);
     cur = __shfl_sync(kFull, cur, 0);
+    int n = 0, row = 0, col = 0;                            // this lane's cell of the current batch
+    if (cur < p.n_batches && cur * 32 + lane < p.n_cells) {
+        const int cell = cur * 32 + lane;
+        n = p.cell_n[cell]; row = (int)p.cell_row[cell]; col = p.cell_col[cell];
+    }
     // zero the other half of the ping-pong for the next launch
     {
         const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gsz = (size_t)gridDim.x * blockDim.x;
@@ -240,12 +252,13 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
         const long long t_begin = clock64();
         const int t_batch = cur;
 #endif
-        const int cell = cur * 32 + lane;
-        const int n = cell < p.n_cells ? p.cell_n[cell] : 0;
-        const int row = cell < p.n_cells ? (int)p.cell_row[cell] : 0;
-        const int col = cell < p.n_cells ? p.cell_col[cell] : 0;
         const bool early = __shfl_sync(kFull, n, 0) <= kNDirect;               // lane 0 holds the batch's largest count
         if (early && lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+#ifdef SG_Z_TIMING
+        long long t_last = t_begin;
+        const int t_large = early ? 0 : 1;
+#endif
+        SG_ZCLK(0)                                          // cell list loads, claim
         const bool valid = n > 0;                           // listed cells have n >= 1; lanes past the end of the list have 0
         const bool bycount_small = n <= kNDirect;
 
@@ -284,6 +297,15 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
             }
             if (bycount_small) for (k = K - 1; k < R; ++k) buf[k * 32] = kInf;   // c_{K-1} is not a threshold
         }
+        // a batch of small counts: its claim has come back by now; fetch the next batch's list entries while this
+        // one draws
+        int nxt = 0, n_nxt = 0, row_nxt = 0, col_nxt = 0;
+        if (early) {
+            nxt = __shfl_sync(kFull, pend, 0);
+            const int cell = nxt * 32 + lane;
+            if (nxt < p.n_batches && cell < p.n_cells) { n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell]; }
+        }
+        SG_ZCLK(1)                                          // staging
         const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
         const bool small = valid && ok && bycount_small;
         int nrem = (valid && ok && !bycount_small) ? n : 0;
@@ -296,10 +318,11 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
             const int tmax = __reduce_max_sync(kFull, small ? n : 0);
             const int nn = small ? n : 0;
             const double Sd = small ? S : -1.0;                                // other lanes search with x < 0: class 0, discarded
-            SG_DISPATCH_NG(ng, z_direct, buf, zc, us, ng, nn, tmax, Sd)
+            SG_DISPATCH_NG(ng, z_direct, buf, us, ng, nn, tmax, Sd, p, zin_s, row, col)
             n_direct += (unsigned)nn;
         }
 
+        SG_ZCLK(2)                                          // direct loop
         // ---- large counts
         if (__any_sync(kFull, nrem > 0)) {
             // visiting order: counting sort of the classes by d = min(7, expo(S) - expo(P*E)), ties by index
@@ -321,6 +344,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                     ord[pos * 32] = (unsigned char)k;
                 }
             }
+            SG_ZCLK(3)                                      // sort
             // conditional binomials in visiting order while more than kNDirect mutations are left;
             // binomial t uses word t&3 of block t>>2
             double rem = S;
@@ -344,6 +368,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                     tl = t + 1;
                 }
             }
+            SG_ZCLK(4)                                      // chain
             if (nrem > 0 && tl == K - 1) {                                      // only the class visited last is left
                 z_emit(p, zin_s, row, col, ord[(K - 1) * 32], nrem);
                 nrem = 0;
@@ -378,7 +403,9 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
             }
         }
 
-        // ---- flush the direct draws' class counts
+        SG_ZCLK(5)                                          // tail
+        // ---- flush the class counts of the draws that finished the chains
+        if (!early)
         for (int w = 0; w < nw; ++w) {
             const unsigned v = zc[w * 32];
             if (v) {
@@ -391,11 +418,17 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
             }
         }
         if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                    // degenerate probabilities
+        SG_ZCLK(6)                                          // flush + emits
 #ifdef SG_Z_TIMING
         if (lane == 0 && t_batch < (1 << 16)) g_z_batch_cycles[t_batch] = (unsigned)(clock64() - t_begin);
 #endif
-        if (!early && lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
-        cur = __shfl_sync(kFull, pend, 0);
+        if (!early) {
+            if (lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+            nxt = __shfl_sync(kFull, pend, 0);
+            const int cell = nxt * 32 + lane;
+            if (nxt < p.n_batches && cell < p.n_cells) { n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell]; }
+        }
+        cur = nxt; n = n_nxt; row = row_nxt; col = col_nxt;
     }
     if (p.draw_count) {
         const unsigned a = __reduce_add_sync(kFull, n_direct), b = __reduce_add_sync(kFull, n_binom);

@@ -1394,6 +1394,10 @@ extern "C" int signer_debug_p_clocks(long long *out, int nblocks)
 {
     return (int)cudaMemcpyFromSymbol(out, sg::g_p_clock, sizeof(long long) * 8 * (size_t)nblocks);
 }
+extern "C" int signer_debug_z_phases(unsigned long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, sg::g_z_phase, sizeof(unsigned long long) * 16);
+}
 extern "C" int signer_debug_batch_cycles(unsigned *out, int n)
 {
     return (int)cudaMemcpyFromSymbol(out, sg::g_z_batch_cycles, sizeof(unsigned) * (size_t)n);
