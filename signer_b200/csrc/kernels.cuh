@@ -86,13 +86,12 @@ struct ZParams {
 };
 
 // per warp: buf [R][32] f64 (cumulative sums or products; R = K rounded up so that the thresholds c_0..c_{K-2} are
-// followed by at least one +inf pad and fill whole groups of four), ord [K][32] u8, zc [ceil(K/4)][32] u32 ; per block: Zin [I*K] i32
+// followed by at least one +inf pad and fill whole groups of four), ord [K][32] u8 ; per block: Zin [I*K] i32
 __host__ __device__ inline int z_groups(int K) { return (K - 1) / 4 + 1; }
 __host__ __device__ inline int z_rows(int K) { return 4 * z_groups(K); }
-inline int z_words(int K) { return (K + 3) / 4; }
 inline size_t z_smem_bytes_per_warp(int K)
 {
-    return (size_t)8 * z_rows(K) * 32 + ((size_t)K * 32 + 7) / 8 * 8 + (size_t)z_words(K) * 32 * 4;
+    return (size_t)8 * z_rows(K) * 32 + ((size_t)K * 32 + 7) / 8 * 8;
 }
 
 SG_D void z_emit(const ZParams &p, int *zin_s, int row, int col, int k, int z)
@@ -100,7 +99,7 @@ SG_D void z_emit(const ZParams &p, int *zin_s, int row, int col, int k, int z)
     if (zin_s) atomicAdd(zin_s + row + p.I * k, z);
     else atomicAdd(p.Zin + (size_t)row + (size_t)p.I * k, z);
     atomicAdd(p.Znj + (size_t)k + (size_t)p.K * col, z);
-    if (p.Zcube) p.Zcube[(size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k)] += (double)z;     // the shard's own cube
+    if (p.Zcube) atomicAdd(p.Zcube + (size_t)row + (size_t)p.I * ((size_t)col + (size_t)p.J * k), (double)z);   // the shard's own cube (small integers: exact in any order)
 }
 
 // Classes of four direct draws on one column c of cumulative sums: class = first k < K-1 with x < c_k, else K-1.
@@ -134,8 +133,6 @@ SG_D void z_search4(const double *c, int ng, const double *ge, double x0, double
     c3 = 4 * g3 + ((v30 <= x3) ? 1 : 0) + ((v31 <= x3) ? 1 : 0) + ((v32 <= x3) ? 1 : 0);
 }
 
-SG_D void z_count(unsigned *zc, int cls) { atomicAdd(zc + (cls >> 2) * 32, 1u << ((cls & 3) * 8)); }
-
 // the direct method for one batch: lane draws nn (0 for lanes that take no part) classes, four per Philox block;
 // draw t uses word t&3 of block t>>2 of the lane's stream.  The group ends stay in registers for the whole cell.
 // Every draw is added to the statistics at once (measured faster than counting per class and flushing: the flush
@@ -164,9 +161,10 @@ SG_D void z_direct(const double *buf, const UStream &us, int ng, int nn, int tma
 // each) are dealt round-robin to the lanes, whoever owns the cell -- a lane reads the owner's column of shared
 // memory and adds to the owner's count bytes.  incl/excl: running totals of the lanes' block counts.
 template <int NG>
-SG_D void z_tail(const double *buf, unsigned *zc, const ZParams &p, int lane, int ng, int incl, int excl, int utot, int nrem,
-                 double Sr, uint32_t elem)
+SG_D void z_tail(const double *buf, const ZParams &p, int *zin_s, int lane, int ng, int incl, int excl, int utot, int nrem,
+                 double Sr, int row, int col)
 {
+    const uint32_t elem = (uint32_t)(row + p.I * (col + p.col0));
     for (int ub = 0; ub < utot; ub += 32) {
         const int g = min(ub + lane, utot - 1);
         const bool act = ub + lane < utot;
@@ -180,13 +178,13 @@ SG_D void z_tail(const double *buf, unsigned *zc, const ZParams &p, int lane, in
         const U4 w = philox4x32_10(kTailBlock0 + (uint32_t)b, elem_o, p.stream, p.sweep, p.key.k0, p.key.k1);
         const int nd = act ? min(4, nr_o - 4 * b) : 0;                         // draws of this block
         const double *buf_o = buf + (o - lane);
-        unsigned *zc_o = zc + (o - lane);
+        const int row_o = __shfl_sync(kFull, row, o), col_o = __shfl_sync(kFull, col, o);
         int c0, c1, c2, c3;
         z_search4<NG>(buf_o, ng, nullptr, u32(w.x) * Sr_o, u32(w.y) * Sr_o, u32(w.z) * Sr_o, u32(w.w) * Sr_o, c0, c1, c2, c3);
-        if (nd > 0) z_count(zc_o, c0);
-        if (nd > 1) z_count(zc_o, c1);
-        if (nd > 2) z_count(zc_o, c2);
-        if (nd > 3) z_count(zc_o, c3);
+        if (nd > 0) z_emit(p, zin_s, row_o, col_o, c0, 1);
+        if (nd > 1) z_emit(p, zin_s, row_o, col_o, c1, 1);
+        if (nd > 2) z_emit(p, zin_s, row_o, col_o, c2, 1);
+        if (nd > 3) z_emit(p, zin_s, row_o, col_o, c3, 1);
     }
 }
 
@@ -217,15 +215,12 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
     double *buf = reinterpret_cast<double *>(base) + lane;              // this lane's column: buf[k * 32]
     const int ng = z_groups(K), R = 4 * ng;                             // groups of four thresholds, rows of buf
     unsigned char *ord = base + (size_t)8 * R * 32 + lane;              // ord[t * 32]: class visited at step t
-    unsigned *zc = reinterpret_cast<unsigned *>(base + (size_t)8 * R * 32 + ((size_t)K * 32 + 7) / 8 * 8) + lane;   // zc[w * 32]: counts of classes 4w..4w+3
     int *zin_s = p.zin_smem ? reinterpret_cast<int *>(smem_raw + (size_t)(blockDim.x >> 5) * p.warp_smem) : nullptr;
-    const int nw = (K + 3) / 4;
 
     if (zin_s) {
         for (int i = tid; i < I * K; i += blockDim.x) zin_s[i] = 0;
         __syncthreads();
     }
-    for (int w = 0; w < nw; ++w) zc[w * 32] = 0;            // invariant: all zero between cells
     const bool vec2 = (K & 1) == 0;
     unsigned n_direct = 0, n_binom = 0;                     // this lane's draw counts (reported only on request)
 
@@ -395,28 +390,14 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
                 const int excl = incl - units;
                 const int utot = __shfl_sync(kFull, incl, 31);
-                const uint32_t elem = (uint32_t)(row + I * (col + p.col0));
                 __syncwarp();
-                SG_DISPATCH_NG(ng, z_tail, buf, zc, p, lane, ng, incl, excl, utot, nrem, Sr, elem)
+                SG_DISPATCH_NG(ng, z_tail, buf, p, zin_s, lane, ng, incl, excl, utot, nrem, Sr, row, col)
                 __syncwarp();
                 n_direct += (unsigned)nrem;
             }
         }
 
         SG_ZCLK(5)                                          // tail
-        // ---- flush the class counts of the draws that finished the chains
-        if (!early)
-        for (int w = 0; w < nw; ++w) {
-            const unsigned v = zc[w * 32];
-            if (v) {
-                zc[w * 32] = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int z = (int)((v >> (8 * b)) & 255u);
-                    if (z) z_emit(p, zin_s, row, col, 4 * w + b, z);
-                }
-            }
-        }
         if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                    // degenerate probabilities
         SG_ZCLK(6)                                          // flush + emits
 #ifdef SG_Z_TIMING
