@@ -347,6 +347,10 @@ def main():
     chain.profile(True)
     chain.run(burn=n_prof, fetch=False)
     prof = chain.profile(False)
+    # ... and of evaluation sweeps (ring stores + log-likelihood), same way
+    chain.profile(True)
+    chain.run(eval=min(n_prof, 200), keep_par=False, fetch=False)
+    prof_eval = chain.profile(False)
     kz = prof["z_alloc_fused"]
     z_ms = kz["ms"] / max(1, kz["launches"])
     tot_prof_ms = sum(v["ms"] for v in prof.values())
@@ -425,6 +429,7 @@ def main():
                     roofline_sweep=dict(algorithmic_bytes_per_sweep=b_sweep, achieved=b_sweep * per_rank_sps / 1e9, peak=peak,
                                         unit="GB/s", frac=b_sweep * per_rank_sps / 1e9 / peak),
                     kernel_ms=kernels_ms,
+                    kernel_ms_eval={k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in prof_eval.items()},
                     draws_per_s=dict(step1_categorical=per_rank_sps * n_cat / n_cnt, step1_binomial=per_rank_sps * n_bin / n_cnt,
                                      gamma=per_rank_sps * 3 * K * (I + J), mh_uniform=per_rank_sps * K * (I + J),
                                      step1_draws_per_sweep=(n_cat + n_bin) / n_cnt,

@@ -22,13 +22,13 @@
  *       k order, zero-probability skip, pp<1 test, early exit at n<=0, remainder to the last class.
  *
  * What it does NOT reproduce: R's RNG stream and R's rbinom/rgamma algorithms (unavailable).
- * Instead every random draw follows the "draw specification v1" below: counter-based
+ * Instead every random draw follows the "draw specification v6" below: counter-based
  * Philox4x32-10 streams addressed by (seed, sweep, step, element, block) and samplers built only
  * from IEEE-754 correctly rounded operations (+ - * / sqrt fma) in a fixed order, so that an
  * independent implementation (the CUDA kernels) can be compared BIT FOR BIT.
  * Compile with -ffp-contract=off (see oracle/Makefile); every fused multiply-add is explicit.
  *
- * Draw specification v1 (shared contract with signer_b200/csrc, written independently there):
+ * Draw specification v6 (shared contract with signer_b200/csrc, written independently there):
  *   stream address: key = (seed_lo, seed_hi); counter = (block, element, stream_id, sweep)
  *   stream ids: 0 permutation, 1..7 Gibbs steps, 8 initial Z
  *   element: step 1/8: i + I*j ; P family (2,4,6): i + I*k ; E family (3,5,7): k + K*j
@@ -36,14 +36,23 @@
  *   u32(w) = (w + 1/2) * 2^-32: step-1 uniforms carry 32 random bits like R's unif_rand (Mersenne-Twister)
  *   step 1, cells with count n <= 32: direct method, n categorical draws; draw t uses word (t&3) of
  *                block (t>>2): x = u*S, class = first k < K-1 with x < c_k, c_k = c_{k-1} + P[i,k]*E[k,j],
- *                else the last class.  Larger cells: sequential conditional binomials (rmultinom), the
- *                classes visited heaviest first (running argmax of P*E, ties to the lowest index):
- *   step 1, conditional binomial number t: the inversion uniform is word (t&3) of block (t>>2);
- *                BTRS attempt a of binomial t reads block 0x1000 + (t<<8) + a (U from word 0, V from word 1)
- *   gamma draws: Marsaglia-Tsang attempt t uses block t: x = ppnd16(u(w0,w1)), accept test u(w2,w3);
- *                block 0xFFFFFFFF gives (boost uniform for shape<1, MH acceptance uniform)
+ *                else the last class.
+ *   step 1, larger cells: sequential conditional binomials (rmultinom's rules); the classes are visited in
+ *                the order of d_k = min(7, expo(S) - expo(P*E)) ascending (expo = biased binary exponent),
+ *                ties lowest index first; conditional binomial number t: the inversion uniform is word (t&3)
+ *                of block (t>>2); BTRS attempt a of binomial t reads block 0x1000 + (t<<8) + a (U from word
+ *                0, V from word 1).  The chain stops once at most 32 mutations are left; those are dealt by
+ *                the direct method over the unvisited classes: c_k in index order with the visited classes'
+ *                P*E set to zero, Sr = c_{K-1}, draw d uses word (d&3) of block 0x800 + (d>>2), x = u*Sr,
+ *                class = first k < K-1 with x < c_k, else K-1.
  *   binomial(n,pp): p=min(pp,1-pp); n*p<30 -> inversion from q^n (binary powering), recurrence
- *                   r <- (r * (s*(n-x+1))) * (1/x); else Hormann BTRS; flip back if pp>0.5
+ *                   r <- r * fma(a, 1/x, -s), s = p/q, a = s*(n+1); else Hormann BTRS; flip back if pp>0.5
+ *   normal:      ziggurat, 128 layers (det_tables.h), see normal_draw
+ *   gamma draws: Marsaglia-Tsang attempt t uses block t: normal from words 0,1 (further blocks
+ *                0x10000 + (t<<8) + q when the fast path fails), accept test u53(w2,w3);
+ *                block 0xFFFFFFFF gives (boost uniform for shape<1, MH acceptance uniform)
+ *   log:         table-driven, division-free (det_tables.h), see oracle_log; exp: fdlibm-style; lgamma: shift to
+ *                >= 8 + 8 Stirling terms
  *   fp reductions: PE = fma chain over k; corrP = fma chain over i; corrE = 128-column segment
  *                  fma chains, segments added in ascending order (per shard, shards ascending);
  *                  loglik = per-column sums in 32-row chunks (chunks added in order), then a

@@ -44,7 +44,7 @@ if os.path.exists(lf):
             f.write("%-40s %8d %14.0f %12.2f %7.1f%%\n" % (k, n, t, t / n / 1e3, 100 * t / s))
     print(open(os.path.join(P, "%s_launch_list.txt" % tag)).read())
 # 2. full captures
-for short, kname in (("z", "z_alloc_fused"), ("e", "e_family")):
+for short, kname in (("z", "z_alloc_fused"), ("e", "e_family"), ("p", "p_family")):
     rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (short, tag))
     if not os.path.exists(rep): continue
     m = raw(rep)

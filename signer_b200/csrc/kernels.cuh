@@ -32,23 +32,24 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 // K1  z_alloc_fused : replaces gibbs_step1 (src/gibbs_2.cpp:85-103) + cube_sum_j/_i (:9-28)
 //
 // The counts M never change during a chain, so the non-zero cells are listed ONCE, sorted by count
-// (largest first; ties in genome-major order), and every launch walks that list: a warp takes 32
-// consecutive cells -- cells of (nearly) the same count, so the lanes run the same sampler with
-// the same trip count -- one thread per cell.  Each lane owns one column of the warp's shared
-// memory: K doubles, K order bytes, K count bytes.
+// (largest first; counts up to 32 by their number of four-draw rounds, ties in genome-major order), and
+// every launch walks that list: a warp takes 32 consecutive cells -- cells of (nearly) the same count,
+// so the lanes run the same sampler with the same trip count -- one thread per cell.  Each lane owns one
+// column of the warp's shared memory: K doubles (padded to whole groups of four) and K order bytes.
 //   * n <= 32 : direct method.  The lane stages the cumulative sums c_k of P[i,k]*E[k,j]; a draw is
-//     x = u*S and a branch-free two-level search (count the group ends <= x, then the thresholds of
-//     that group), four draws per Philox block searched together so their shared-memory loads overlap.
+//     x = u*S and a branch-free two-level search (count the group ends <= x -- kept in registers for the
+//     cell -- then the thresholds of that group), four draws per Philox block searched together.
 //   * n  > 32 : the lane stages the products themselves, sorts the classes by binary order of
 //     magnitude (counting sort on the exponent distance to S: heavy classes first), runs R's
 //     conditional-binomial chain in that order while more than 32 mutations are left (inversion
-//     below n*p < 30, BTRS above), and deals the remainder to the unvisited classes by the direct
-//     method (linear scan in visiting order: the heavy classes come first).
-// Class counts of the direct draws are kept in the lane's count bytes (shared-memory adds without a
-// read-back) and flushed once per cell; Z is never written (except, on request, the final sweep's
-// cube for the reference's `Zs`): sum_j Z goes to a block-wide shared-memory Zin (integer atomics,
-// flushed once per block) and sum_i Z straight to L2 integer atomics.  Batches are claimed
-// heaviest-first from a global counter, one ahead of the batch being processed.
+//     below n*p < 30, BTRS above), and the remainder goes to the unvisited classes by the direct
+//     method on the cumulative sums in index order with the visited classes zeroed -- that part is
+//     shared by the whole warp (the cells' Philox blocks are dealt round-robin to the lanes).
+// Z is never written (except, on request, the final sweep's cube for the reference's `Zs`): every
+// direct draw and every chain step adds to the sufficient statistics at once -- sum_j Z to a
+// block-wide shared-memory Zin (integer atomics, flushed once per block), sum_i Z straight to L2
+// integer atomics.  Batches are claimed heaviest-first from a global counter; a batch of small counts
+// claims its successor and fetches its list entries while it draws.
 // ------------------------------------------------------------------------------------------------
 constexpr int kZMaxWarps = 24;   // most warps per block; the host picks the block size per K (z_pick_block) -- the warps of a
                                  // block share only its Zin accumulator
@@ -58,11 +59,8 @@ constexpr int kZinSmemMax = 40 * 1024;
 #ifndef SG_STAGE_UNROLL
 #define SG_STAGE_UNROLL 2
 #endif
-#ifndef SG_NTAIL
-#define SG_NTAIL 32
-#endif
 constexpr int kStageUnroll = SG_STAGE_UNROLL;
-constexpr int kNTail = SG_NTAIL;      // a chain stops once this few mutations are left; they are dealt by the direct method
+constexpr int kNTail = 32;          // a chain stops once this few mutations are left; they are dealt by the direct method
 constexpr uint32_t kTailBlock0 = 0x800u;   // first Philox block of the direct draws that finish a chain
 
 struct ZParams {
@@ -712,61 +710,123 @@ struct LLParams {
     const double *W, *P, *E;
     double *col;                // [n2]
     int mode;
+    // optional: the block that finishes last also runs the stride-halving tree over tree_a[0..n2) and writes
+    // out[0] = tree_a[0] - sub[0] (one launch fewer per evaluation sweep); tree_a = null: tree_sum does it
+    double *tree_a;
+    int n2;
+    const double *sub;
+    double *out;
+    unsigned *ticket;           // zero before the launch; reset by the last block
 };
 
-__global__ void __launch_bounds__(128) loglik_cols(const LLParams p)
+constexpr int kLLWarps = 8;       // warps per block
+constexpr int kLLRound = 96;      // rows per round: three chunks; every warp evaluates 12 rows of a round
+
+// 32 genomes per block, lanes = genomes.  A round covers 96 rows: warp w evaluates the terms of rows 12w .. 12w+11
+// (four rows in flight: four independent fma chains over k) into shared memory; then the first three warps add the
+// terms of one chunk each in row order, and the first warp adds the chunk sums to the genome's total in chunk order.
+inline size_t loglik_smem_bytes(int K) { return sizeof(double) * ((size_t)K * 33 + (size_t)kLLRound * 33 + 3 * 32); }
+
+__global__ void __launch_bounds__(32 * kLLWarps, 3) loglik_cols(const LLParams p)
 {
-    // 32 genomes per block.  The terms of a 32-row chunk are evaluated by all 128 threads (8 rows each)
-    // into shared memory, then one thread per genome adds them in row order, chunk after chunk.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int I = p.I, J = p.J, K = p.K;
-    const int nchunk = (I + kLLChunk - 1) / kLLChunk;
     double *E_s = reinterpret_cast<double *>(smem_raw);   // [K][33]
-    double *P_s = E_s + K * 33;                           // [32][K]
-    double *term = P_s + kLLChunk * K;                    // [32][33]
-    const int tid = threadIdx.x, lane = tid & 31, rl = tid >> 5;
-    const int j0 = blockIdx.x * 32, j = j0 + lane;
+    double *term = E_s + K * 33;                          // [kLLRound][33]
+    double *csum = term + kLLRound * 33;                  // [3][32]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int j0 = blockIdx.x * 32, j = j0 + lane, jc = min(j, J - 1);
     if (p.mode == 0) {
-        for (int idx = tid; idx < K * 32; idx += 128) {
+        for (int idx = tid; idx < K * 32; idx += 32 * kLLWarps) {
             const int jj = idx / K, k = idx - jj * K;
             E_s[k * 33 + jj] = (j0 + jj < J) ? p.E[(size_t)K * j0 + idx] : 0.0;
         }
     }
     double a = 0.0;
-    for (int c = 0; c < nchunk; ++c) {
-        const int i0 = c * kLLChunk, rows = min(kLLChunk, I - i0);
-        __syncthreads();
-        if (p.mode == 0)
-            for (int idx = tid; idx < kLLChunk * K; idx += 128) {
-                const int r = idx & 31, k = idx >> 5;
-                P_s[r * K + k] = (r < rows) ? p.P[(size_t)(i0 + r) + (size_t)I * k] : 0.0;
-            }
-        __syncthreads();
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = rl * 8 + rr, i = i0 + r;
-            double t = 0.0;
-            if (r < rows && j < J) {
-                const double m = (double)p.M[(size_t)i * p.Jp + j];
-                if (p.mode == 0) {
-                    const double *Pr = P_s + r * K;
-                    double pe = 0.0;
-                    for (int k = 0; k < K; ++k) pe = fma(Pr[k], E_s[k * 33 + lane], pe);
-                    const double lam = pe * p.W[(size_t)i * p.Jp + j];
-                    t = m * det_log(lam) - lam;
-                } else {
-                    t = det_lgamma(m + 1.0);
+    for (int i0 = 0; i0 < I; i0 += kLLRound) {
+        __syncthreads();                                  // E_s staged; term / csum of the previous round consumed
+        for (int g = 0; g < 3; ++g) {
+            const int rb = 12 * w + 4 * g, ib = i0 + rb;  // four rows ib .. ib+3 (clamped; rows beyond I are not added)
+            if (ib >= I) break;
+            const int ia = ib, ib1 = min(ib + 1, I - 1), ic = min(ib + 2, I - 1), id = min(ib + 3, I - 1);
+            const double ma = (double)p.M[(size_t)ia * p.Jp + jc], mb = (double)p.M[(size_t)ib1 * p.Jp + jc];
+            const double mc = (double)p.M[(size_t)ic * p.Jp + jc], md = (double)p.M[(size_t)id * p.Jp + jc];
+            double ta, tb, tc, td;
+            if (p.mode == 0) {
+                const double wa = p.W[(size_t)ia * p.Jp + jc], wb = p.W[(size_t)ib1 * p.Jp + jc];
+                const double wc = p.W[(size_t)ic * p.Jp + jc], wd = p.W[(size_t)id * p.Jp + jc];
+                double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
+                const double *Pk = p.P;
+                double qa = __ldg(Pk + ia), qb = __ldg(Pk + ib1), qc = __ldg(Pk + ic), qd = __ldg(Pk + id);
+                for (int k = 0; k < K; ++k) {                                 // the next class's P values load while this one's fmas run
+                    const double e = E_s[k * 33 + lane];
+                    const double ra = qa, rb2 = qb, rc = qc, rd = qd;
+                    if (k + 1 < K) {
+                        Pk += I;
+                        qa = __ldg(Pk + ia); qb = __ldg(Pk + ib1); qc = __ldg(Pk + ic); qd = __ldg(Pk + id);
+                    }
+                    pa = fma(ra, e, pa); pb = fma(rb2, e, pb); pc = fma(rc, e, pc); pd = fma(rd, e, pd);
                 }
+                const double la = pa * wa, lb = pb * wb, lc = pc * wc, ld = pd * wd;
+                ta = ma * det_log(la) - la; tb = mb * det_log(lb) - lb;
+                tc = mc * det_log(lc) - lc; td = md * det_log(ld) - ld;
+            } else {
+                ta = det_lgamma(ma + 1.0); tb = det_lgamma(mb + 1.0);
+                tc = det_lgamma(mc + 1.0); td = det_lgamma(md + 1.0);
             }
-            term[r * 33 + lane] = t;
+            term[rb * 33 + lane] = ta; term[(rb + 1) * 33 + lane] = tb;
+            term[(rb + 2) * 33 + lane] = tc; term[(rb + 3) * 33 + lane] = td;
         }
         __syncthreads();
-        if (tid < 32) {
+        if (w < 3) {
+            const int r0 = 32 * w, rows = min(kLLChunk, I - (i0 + r0));
             double ac = 0.0;
-            for (int r = 0; r < rows; ++r) ac = ac + term[r * 33 + tid];
-            a = a + ac;
+            for (int r = 0; r < rows; ++r) ac = ac + term[(r0 + r) * 33 + lane];
+            csum[w * 32 + lane] = ac;
+        }
+        __syncthreads();
+        if (w == 0) {
+            const int nc = min(3, (I - i0 + kLLChunk - 1) / kLLChunk);
+            for (int cc = 0; cc < nc; ++cc) a = a + csum[cc * 32 + lane];
         }
     }
-    if (tid < 32 && j < J) p.col[j] = a;
+    if (w == 0 && j < J) p.col[j] = a;
+    if (!p.tree_a) return;
+    // ---- last block: a[t] += a[t+s] for s = n2/2 .. 1 (the arithmetic of tree_sum), levels below 2048 in shared memory
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double *ta = p.tree_a;
+    double *sh = reinterpret_cast<double *>(smem_raw);    // 2048 doubles fit: the term array alone is 96 * 33
+    int sdist = p.n2 >> 1;
+    for (; sdist >= 2048; sdist >>= 1) {                  // eight independent pairs in flight per thread
+        for (int t0 = tid; t0 < sdist; t0 += 8 * 32 * kLLWarps) {
+            double x[8], y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * 32 * kLLWarps;
+                if (t < sdist) { x[u] = ta[t]; y[u] = ta[t + sdist]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * 32 * kLLWarps;
+                if (t < sdist) ta[t] = x[u] + y[u];
+            }
+        }
+        __syncthreads();
+    }
+    const int mlen = min(p.n2, 2048);
+    for (int t = tid; t < mlen; t += 32 * kLLWarps) sh[t] = ta[t];
+    __syncthreads();
+    for (sdist = mlen >> 1; sdist >= 1; sdist >>= 1) {
+        for (int t = tid; t < sdist; t += 32 * kLLWarps) sh[t] = sh[t] + sh[t + sdist];
+        __syncthreads();
+    }
+    if (tid == 0) { p.out[0] = p.sub ? sh[0] - p.sub[0] : sh[0]; *p.ticket = 0u; }
 }
 
 // a[t] += a[t+s] for s = n2/2 .. 1 ; result written to out[0] = a[0] - sub (sub may be null).

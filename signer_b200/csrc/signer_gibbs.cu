@@ -168,9 +168,8 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
         double *col = nullptr;
         CU(cudaMalloc(&col, (size_t)d->n2 * sizeof(double)));
         CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
-        LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1};
-        const size_t smem = sizeof(double) * (size_t)(1 * 33 + kLLChunk * 1 + kLLChunk * 33);
-        loglik_cols<<<(J + 31) / 32, 128, smem>>>(lp);
+        LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1, nullptr, 0, nullptr, nullptr, nullptr};
+        loglik_cols<<<(J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(1)>>>(lp);
         tree_sum<<<1, 1024>>>(col, d->n2, nullptr, d->lgm);
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
@@ -231,6 +230,7 @@ struct signer_chain {
     unsigned long long *draw_count = nullptr;    // [2] device counters of step-1 draws (allocated on request)
     double *acache_p = nullptr, *acache_e = nullptr;   // [3][I*K], [3][K*J]: A-only terms of the MH ratios (kernels.cuh, ACache)
     unsigned long long *tile_counter = nullptr;
+    unsigned *ll_ticket = nullptr;               // block counter of loglik_cols' fused tree
     unsigned long long z_launches = 0;
     int z_grid = 0, z_warps = 8, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
     int ksplit = 1;
@@ -257,7 +257,7 @@ struct signer_chain {
             cudaFree(Zin[b]); cudaFree(Znj[b]);
             free_ring(ring[b]);
         }
-        cudaFree(tile_counter); cudaFree(draw_count);
+        cudaFree(tile_counter); cudaFree(draw_count); cudaFree(ll_ticket);
         for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -369,11 +369,12 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     return SIGNER_OK;
 }
 
-int launch_loglik_cols(signer_chain *c)
+// per-genome log-likelihood terms; with `out` the last block also runs the tree (unsharded chains)
+int launch_loglik_cols(signer_chain *c, double *out = nullptr)
 {
-    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col + c->col0, 0};
-    const size_t smem = sizeof(double) * (size_t)(c->K * 33 + kLLChunk * c->K + kLLChunk * 33);
-    loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
+    LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col + c->col0, 0,
+                out ? c->col : nullptr, c->data->n2, c->data->lgm, out, c->ll_ticket};
+    loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(c->K), c->stream>>>(lp);
     c->launches++;
     CU(cudaGetLastError());
     return SIGNER_OK;
@@ -382,11 +383,7 @@ int launch_loglik_cols(signer_chain *c)
 int launch_loglik(signer_chain *c, double *out)
 {
     ProfScope ps(c, 3);
-    ST(launch_loglik_cols(c));
-    tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out);
-    c->launches++;
-    CU(cudaGetLastError());
-    return SIGNER_OK;
+    return launch_loglik_cols(c, out);
 }
 
 // Touch every page of a caller-allocated output buffer (it is ours to overwrite) so that the later
@@ -596,6 +593,8 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)data->n2, c->stream));
     CU(cudaMalloc(&c->tile_counter, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned long long), c->stream));
+    CU(cudaMalloc(&c->ll_ticket, sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->ll_ticket, 0, sizeof(unsigned), c->stream));
     CU(cudaMalloc(&c->stats, 8 * sizeof(double)));
     CU(cudaMalloc(&c->acache_p, 3 * c->nP * sizeof(double)));
     CU(cudaMalloc(&c->acache_e, 3 * c->nE * sizeof(double)));
@@ -875,9 +874,8 @@ int shard_loglik(ShardSet &S, int mode_lgm, double *out0)
         CU(cudaSetDevice(c->device));
         CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)c->data->n2, c->stream));
         if (mode_lgm) {
-            LLParams lp{c->I, c->J, c->Jp, 1, c->data->Mrow, c->data->W, nullptr, nullptr, c->col + c->col0, 1};
-            const size_t smem = sizeof(double) * (size_t)(1 * 33 + kLLChunk * 1 + kLLChunk * 33);
-            loglik_cols<<<(c->J + 31) / 32, 128, smem, c->stream>>>(lp);
+            LLParams lp{c->I, c->J, c->Jp, 1, c->data->Mrow, c->data->W, nullptr, nullptr, c->col + c->col0, 1, nullptr, 0, nullptr, nullptr, nullptr};
+            loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(1), c->stream>>>(lp);
             CU(cudaGetLastError());
         } else {
             ST(launch_loglik_cols(c));
