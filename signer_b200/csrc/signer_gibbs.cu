@@ -241,6 +241,11 @@ struct signer_chain {
     int64_t launches = 0;
     int Pfixed = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    // the log-likelihood of an evaluation sweep only reads P and E: it runs on its own stream next to the following
+    // sweep's z_alloc_fused (which reads them too); the next kernel that writes P or E waits for it
+    cudaStream_t ll_stream = nullptr;
+    cudaEvent_t ll_ready = nullptr, ll_done = nullptr;
+    bool ll_pending = false;
     Ring ring[2];
     int ring_cap = 0, ring_keep = 0;
     int last_eval = 0;
@@ -252,6 +257,7 @@ struct signer_chain {
         cudaSetDevice(device);
         if (own_stream) cudaStreamSynchronize(own_stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (ll_stream) cudaStreamSynchronize(ll_stream);
         for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats, sumPs, sumEs, acache_p, acache_e}) cudaFree(p);
         for (int b = 0; b < 2; ++b) {
             cudaFree(Zin[b]); cudaFree(Znj[b]);
@@ -261,6 +267,9 @@ struct signer_chain {
         for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ll_stream) cudaStreamDestroy(ll_stream);
+        if (ll_ready) cudaEventDestroy(ll_ready);
+        if (ll_done) cudaEventDestroy(ll_done);
     }
     static void free_ring(Ring &r)
     {
@@ -274,20 +283,29 @@ struct signer_chain {
 namespace {
 
 struct ProfScope {
-    signer_chain *c; int cls; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(signer_chain *c_, int cls_) : c(c_), cls(cls_)
+    signer_chain *c; int cls; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(signer_chain *c_, int cls_, cudaStream_t st_ = nullptr) : c(c_), cls(cls_), st(st_ ? st_ : c_->stream)
     {
         if (!c->profiling) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~ProfScope()
     {
         if (!c->profiling) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->ev[cls].emplace_back(a, b);
     }
 };
+
+// a kernel that writes P or E is about to be enqueued: the pending log-likelihood must have read them
+int wait_loglik(signer_chain *c)
+{
+    if (!c->ll_pending) return SIGNER_OK;
+    CU(cudaStreamWaitEvent(c->stream, c->ll_done, 0));
+    c->ll_pending = false;
+    return SIGNER_OK;
+}
 
 void host_perm(uint64_t seed, uint32_t sweep, int order[7])
 {
@@ -340,6 +358,7 @@ int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double
     p.Ps_slot = Ps; p.Aps_slot = Aps; p.Bps_slot = Bps;
     p.acache = ACache{c->acache_p, c->acache_p + c->nP, c->acache_p + 2 * c->nP};
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
+    ST(wait_loglik(c));
     {
         ProfScope ps(c, 1);
         p_family<<<(p.IK + 127) / 128, 128, 0, c->stream>>>(p);
@@ -360,6 +379,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     p.Es_slot = Es; p.Aes_slot = Aes; p.Bes_slot = Bes;
     p.acache = ACache{c->acache_e, c->acache_e + c->nE, c->acache_e + 2 * c->nE};
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
+    ST(wait_loglik(c));
     {
         ProfScope ps(c, 2);
         e_family<<<dim3(c->n_seg, c->ksplit), kEThreads, 0, c->stream>>>(p);
@@ -370,20 +390,29 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
 }
 
 // per-genome log-likelihood terms; with `out` the last block also runs the tree (unsharded chains)
-int launch_loglik_cols(signer_chain *c, double *out = nullptr)
+int launch_loglik_cols(signer_chain *c, double *out = nullptr, cudaStream_t st = nullptr)
 {
     LLParams lp{c->I, c->J, c->Jp, c->K, c->data->Mrow, c->data->W, c->P, c->E, c->col + c->col0, 0,
                 out ? c->col : nullptr, c->data->n2, c->data->lgm, out, c->ll_ticket};
-    loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(c->K), c->stream>>>(lp);
+    loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(c->K), st ? st : c->stream>>>(lp);
     c->launches++;
     CU(cudaGetLastError());
     return SIGNER_OK;
 }
 
+// log-likelihood of the current state into out[0], on the side stream (see signer_chain::ll_stream)
 int launch_loglik(signer_chain *c, double *out)
 {
-    ProfScope ps(c, 3);
-    return launch_loglik_cols(c, out);
+    ST(wait_loglik(c));                                    // one in flight at a time: they share col and the ticket
+    CU(cudaEventRecord(c->ll_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->ll_stream, c->ll_ready, 0));
+    {
+        ProfScope ps(c, 3, c->ll_stream);
+        ST(launch_loglik_cols(c, out, c->ll_stream));
+    }
+    CU(cudaEventRecord(c->ll_done, c->ll_stream));
+    c->ll_pending = true;
+    return SIGNER_OK;
 }
 
 // Touch every page of a caller-allocated output buffer (it is ours to overwrite) so that the later
@@ -573,6 +602,9 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->sweep0 = o->sweep0; c->Pfixed = o->Pfixed ? 1 : 0;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->ll_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ll_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ll_done, cudaEventDisableTiming));
     c->stream = c->own_stream;
     auto up = [&](double **dst, const double *src, size_t n) -> int {
         CU(cudaMalloc(dst, n * sizeof(double)));
@@ -730,6 +762,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         }
         c->sweeps_done++;
     }
+    ST(wait_loglik(c));                                    // the launching stream ends after the last log-likelihood
     c->last_eval = eval;
     if (out && eval > 0) {
         CU(cudaStreamSynchronize(c->stream));
