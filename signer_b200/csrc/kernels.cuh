@@ -56,10 +56,6 @@ constexpr int kZMaxWarps = 24;   // most warps per block; the host picks the blo
 constexpr int kZChunk = 1;        // batches of 32 cells per claim
 constexpr int kNDirect = 32;      // largest count drawn by the direct method
 constexpr int kZinSmemMax = 40 * 1024;
-#ifndef SG_STAGE_UNROLL
-#define SG_STAGE_UNROLL 2
-#endif
-constexpr int kStageUnroll = SG_STAGE_UNROLL;
 constexpr int kNTail = 32;          // a chain stops once this few mutations are left; they are dealt by the direct method
 constexpr uint32_t kTailBlock0 = 0x800u;   // first Philox block of the direct draws that finish a chain
 
@@ -261,7 +257,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
         double S = 0.0, c = 0.0;
         {
             int k = 0;
-#pragma unroll kStageUnroll
+#pragma unroll 2
             for (; k + 4 <= K; k += 4) {                    // four classes per round, their loads issued together
                 double e0, e1, e2, e3;
                 if (vec2) {
@@ -442,12 +438,9 @@ SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, doubl
 // in a per-element cache: A changes only when a proposal is accepted, and then its terms are exactly the
 // y-terms just evaluated.  Same operations on the same operands, so the result is bit-identical to
 // re-evaluating them (which is what the oracle does).
-struct ACache { double *lg1, *lg2, *lg; };
-#ifndef SG_UPDATE_A_INLINE
-#define SG_UPDATE_A_INLINE SG_D
-#endif     // lgamma(A+1), lgamma(A*A/var), log(A)
+struct ACache { double *lg1, *lg2, *lg; };     // lgamma(A+1), lgamma(A*A/var), log(A)
 
-SG_UPDATE_A_INLINE double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var,
+SG_D double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var,
                                         const ACache c, size_t ci)
 {
     UStream us; us.init(key, sweep, stream, e);

@@ -130,13 +130,23 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
             const int i = cells[t] % I, j = cells[t] / I;
             cnt[t] = m[(size_t)i * d->Jp + j];
         }
-        std::vector<size_t> idx(nz);
-        for (size_t t = 0; t < nz; ++t) idx[t] = t;
         // sort key: counts above kNDirect by value; smaller ones by their number of direct-method rounds (four
         // draws per Philox block), so that cells that cost the same stay in genome-major order and a warp's lanes
-        // read few distinct columns of E
+        // read few distinct columns of E.  Counting sort (stable) when the keys are small enough.
         auto key = [&](size_t t) { return cnt[t] > kNDirect ? cnt[t] : (g_sort_rounds ? 4 * ((cnt[t] + 3) / 4) : cnt[t]); };
-        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return key(a) > key(b); });
+        std::vector<size_t> idx(nz);
+        int kmax = 0;
+        for (size_t t = 0; t < nz; ++t) kmax = std::max(kmax, key(t));
+        if (kmax <= (1 << 22)) {
+            std::vector<size_t> pos((size_t)kmax + 2, 0);
+            for (size_t t = 0; t < nz; ++t) pos[(size_t)key(t)]++;
+            size_t run = 0;
+            for (int v = kmax; v >= 0; --v) { const size_t h = pos[(size_t)v]; pos[(size_t)v] = run; run += h; }
+            for (size_t t = 0; t < nz; ++t) idx[pos[(size_t)key(t)]++] = t;
+        } else {
+            for (size_t t = 0; t < nz; ++t) idx[t] = t;
+            std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return key(a) > key(b); });
+        }
         crow.reserve(nz + 4096); ccol.reserve(nz + 4096); cn.reserve(nz + 4096);
         size_t t = 0;
         while (t < nz) {
