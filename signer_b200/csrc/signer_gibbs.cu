@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdio>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cstring>
 #include <dlfcn.h>
 #include <functional>
@@ -217,6 +219,85 @@ int ensure_device_setup(int device)
 struct Ring {
     double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr;
     cudaEvent_t filled = nullptr, copied = nullptr;
+    std::shared_ptr<std::atomic<int>> inflight = std::make_shared<std::atomic<int>>(0);   // copy-out jobs not yet done
+};
+
+// ------------------------------------------------------------------------------------------------
+// Copy-out pool.  The caller's output arrays are pageable (R vectors, NumPy arrays); a device-to-host copy
+// straight into them stages through the driver and blocks the enqueuing thread, which starves the GPU of
+// sweeps.  Instead the samples leave in pieces of at most kStageBytes: a worker thread waits for the ring
+// set to be filled, copies a piece into its own pinned buffer at PCIe speed and then moves it into the
+// caller's array, several pieces in flight.  One pool per device, started on first use, never torn down.
+// ------------------------------------------------------------------------------------------------
+class CopyPool {
+public:
+    static constexpr size_t kStageBytes = size_t(32) << 20;
+    static constexpr int kWorkers = 4;
+    struct Job { const char *src; char *dst; size_t bytes; cudaEvent_t ready; std::shared_ptr<std::atomic<int>> pending; };
+
+    static CopyPool &of(int device)
+    {
+        static std::mutex mu;
+        static CopyPool *pools[64] = {nullptr};
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pools[device]) pools[device] = new CopyPool(device);
+        return *pools[device];
+    }
+    // copy [src, src+bytes) (device) to dst (pageable host) once `ready` has happened
+    void post(const void *src, void *dst, size_t bytes, cudaEvent_t ready, const std::shared_ptr<std::atomic<int>> &pending)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t off = 0; off < bytes; off += kStageBytes) {
+            pending->fetch_add(1);
+            q_.push_back(Job{static_cast<const char *>(src) + off, static_cast<char *>(dst) + off, std::min(kStageBytes, bytes - off), ready, pending});
+        }
+        cv_.notify_all();
+    }
+    // block until every job counted by `pending` is done; false if a worker met a CUDA error
+    bool wait(const std::shared_ptr<std::atomic<int>> &pending)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending->load() == 0; });
+        return !failed_;
+    }
+    const char *error() const { return err_; }
+
+private:
+    explicit CopyPool(int device) : device_(device)
+    {
+        for (int w = 0; w < kWorkers; ++w) std::thread([this] { run(); }).detach();
+    }
+    void run()
+    {
+        void *stage = nullptr;
+        cudaStream_t st = nullptr;
+        bool ok = cudaSetDevice(device_) == cudaSuccess && cudaHostAlloc(&stage, kStageBytes, cudaHostAllocDefault) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return !q_.empty(); });
+                j = q_.front(); q_.pop_front();
+            }
+            cudaError_t e = ok ? cudaEventSynchronize(j.ready) : cudaErrorUnknown;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(stage, j.src, j.bytes, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e == cudaSuccess) std::memcpy(j.dst, stage, j.bytes);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (e != cudaSuccess) { failed_ = true; err_ = cudaGetErrorString(e); }
+                j.pending->fetch_sub(1);
+            }
+            done_.notify_all();
+        }
+    }
+    int device_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Job> q_;
+    bool failed_ = false;
+    const char *err_ = "";
 };
 
 } // namespace
@@ -536,20 +617,26 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
     return SIGNER_OK;
 }
 
-// copy chunk `chunk` (sweeps r0 .. r0+cnt-1 of the eval phase) from its ring set to the host
+// copy chunk `chunk` (sweeps r0 .. r0+cnt-1 of the eval phase) from its ring set to the host: posted to the
+// device's copy-out pool, which waits for the ring set's `filled` event
 int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signer_outputs *out)
 {
     Ring &r = c->ring[chunk & 1];
-    CU(cudaStreamWaitEvent(c->copy_stream, r.filled, 0));
-    auto cp = [&](double *dst, const double *src, size_t per) -> int {
-        if (!dst || !src) return SIGNER_OK;
-        CU(cudaMemcpyAsync(dst + per * (size_t)r0, src, sizeof(double) * per * (size_t)cnt, cudaMemcpyDeviceToHost, c->copy_stream));
-        return SIGNER_OK;
+    CopyPool &pool = CopyPool::of(c->device);
+    auto cp = [&](double *dst, const double *src, size_t per) {
+        if (!dst || !src) return;
+        pool.post(src, dst + per * (size_t)r0, sizeof(double) * per * (size_t)cnt, r.filled, r.inflight);
     };
-    if (!c->sumPs) { ST(cp(out->Ps, r.Ps, c->nP)); ST(cp(out->Es, r.Es, c->nE)); }   // else: from the full-length stores at the end
-    ST(cp(out->Bps, r.Bps, c->nP)); ST(cp(out->Bes, r.Bes, c->nE));
-    if (keep_par) { ST(cp(out->Aps, r.Aps, c->nP)); ST(cp(out->Aes, r.Aes, c->nE)); }
-    CU(cudaEventRecord(r.copied, c->copy_stream));
+    if (!c->sumPs) { cp(out->Ps, r.Ps, c->nP); cp(out->Es, r.Es, c->nE); }   // else: from the full-length stores at the end
+    cp(out->Bps, r.Bps, c->nP); cp(out->Bes, r.Bes, c->nE);
+    if (keep_par) { cp(out->Aps, r.Aps, c->nP); cp(out->Aes, r.Aes, c->nE); }
+    return SIGNER_OK;
+}
+
+// the ring set's samples have all reached the caller's arrays (it may be refilled)
+int wait_ring(signer_chain *c, Ring &r)
+{
+    if (!CopyPool::of(c->device).wait(r.inflight)) return fail(SIGNER_ERR_CUDA, CopyPool::of(c->device).error());
     return SIGNER_OK;
 }
 
@@ -735,10 +822,21 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         const size_t R = (size_t)eval;
         double *bufs[7] = {out->Es, out->Bes, keep_par ? out->Aes : nullptr, out->Ps, out->Bps, keep_par ? out->Aps : nullptr, zcube ? out->Zs : nullptr};
         const size_t lens[7] = {c->nE * R, c->nE * R, c->nE * R, c->nP * R, c->nP * R, c->nP * R, (size_t)c->I * c->J * c->K};
-        for (int b = 0; b < 7; ++b)
-            if (bufs[b] && lens[b] * sizeof(double) >= (size_t(8) << 20)) faulters.emplace_back(prefault, bufs[b], lens[b]);
+        // large arrays are touched by several threads each (page faults scale across threads)
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        const size_t max_threads = std::min<size_t>(32, hw / 2);
+        size_t big_bytes = 0;
+        for (int b = 0; b < 7; ++b) if (bufs[b] && lens[b] * sizeof(double) >= (size_t(8) << 20)) big_bytes += lens[b] * sizeof(double);
+        for (int b = 0; b < 7; ++b) {
+            if (!bufs[b] || lens[b] * sizeof(double) < (size_t(8) << 20)) continue;
+            const size_t parts = std::max<size_t>(1, std::min<size_t>(max_threads, max_threads * (lens[b] * sizeof(double)) / big_bytes));
+            const size_t step = ((lens[b] + parts - 1) / parts + 511) / 512 * 512;       // whole pages
+            for (size_t off = 0; off < lens[b]; off += step) faulters.emplace_back(prefault, bufs[b] + off, std::min(step, lens[b] - off));
+        }
     }
     struct Joiner { std::function<void()> f; ~Joiner() { f(); } } joiner{join_faulters};
+    // whatever way this call ends, no copy-out job may outlive it: they write into the caller's arrays
+    Joiner drain{[c, out]() { if (out) { CopyPool &p = CopyPool::of(c->device); p.wait(c->ring[0].inflight); p.wait(c->ring[1].inflight); } }};
     for (int k = 0; k < total; ++k) {
         const uint32_t sweep = c->sweep0 + (uint32_t)c->sweeps_done;
         int order[7];
@@ -750,7 +848,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         } else {
             const int r = k - burn, chunk = r / cap, slot = r % cap;
             Ring &rg = c->ring[chunk & 1];
-            if (slot == 0 && chunk >= 2 && out) CU(cudaStreamWaitEvent(c->stream, rg.copied, 0));
+            if (slot == 0 && chunk >= 2 && out) ST(wait_ring(c, rg));          // the set's previous chunk has left the device
             Slots s;
             s.Ps = rg.Ps + c->nP * slot; s.Es = rg.Es + c->nE * slot;
             s.Bps = rg.Bps + c->nP * slot; s.Bes = rg.Bes + c->nE * slot;
@@ -762,11 +860,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             ST(launch_loglik(c, c->ll_ring + r));
             if (slot == cap - 1 || last) {
                 CU(cudaEventRecord(rg.filled, c->stream));
-                if (out) {
-                    join_faulters();
-                    if (chunk >= 1) ST(flush_chunk(c, chunk - 1, chunk_r0 - cap, cap, keep_par, out));
-                    if (last) ST(flush_chunk(c, chunk, chunk_r0, slot + 1, keep_par, out));
-                }
+                if (out) ST(flush_chunk(c, chunk, chunk_r0, slot + 1, keep_par, out));
                 chunk_r0 += cap;
             }
         }
@@ -777,6 +871,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     if (out && eval > 0) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
+        ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1]));
         join_faulters();
         if (zcube && out->Zs) {
             // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined
