@@ -16,6 +16,8 @@ One JSON line on stdout (rank 0).  Keys beyond the base contract:
                    M, W, the I x J x K cube Z and the state go in, the sample cubes come back
                    (burn = eval = K/2, keep_par = FALSE: the reference's model-selection call,
                    R/signeR.R:164-168), host<->device copies inside the timed region
+  kernel_ms, kernel_ms_eval   mean launch time of each kernel in burn-in / evaluation sweeps (second and third pass
+                   with CUDA events around every launch)
   roofline         dominant kernel z_alloc_fused: algorithmic bytes per launch / mean launch time
   cpu_baseline     the CPU oracle (oracle/, a port: the reference cannot be built here) on this box
 """

@@ -218,7 +218,7 @@ int ensure_device_setup(int device)
 
 struct Ring {
     double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr;
-    cudaEvent_t filled = nullptr, copied = nullptr;
+    cudaEvent_t filled = nullptr;
     std::shared_ptr<std::atomic<int>> inflight = std::make_shared<std::atomic<int>>(0);   // copy-out jobs not yet done
 };
 
@@ -331,7 +331,7 @@ struct signer_chain {
     int64_t sweeps_done = 0;
     int64_t launches = 0;
     int Pfixed = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
     // the log-likelihood of an evaluation sweep only reads P and E: it runs on its own stream next to the following
     // sweep's z_alloc_fused (which reads them too); the next kernel that writes P or E waits for it
     cudaStream_t ll_stream = nullptr;
@@ -347,7 +347,6 @@ struct signer_chain {
     {
         cudaSetDevice(device);
         if (own_stream) cudaStreamSynchronize(own_stream);
-        if (copy_stream) cudaStreamSynchronize(copy_stream);
         if (ll_stream) cudaStreamSynchronize(ll_stream);
         for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats, sumPs, sumEs, acache_p, acache_e}) cudaFree(p);
         for (int b = 0; b < 2; ++b) {
@@ -357,7 +356,6 @@ struct signer_chain {
         cudaFree(tile_counter); cudaFree(draw_count); cudaFree(ll_ticket);
         for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream) cudaStreamDestroy(own_stream);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ll_stream) cudaStreamDestroy(ll_stream);
         if (ll_ready) cudaEventDestroy(ll_ready);
         if (ll_done) cudaEventDestroy(ll_done);
@@ -366,7 +364,6 @@ struct signer_chain {
     {
         for (double *p : {r.Ps, r.Es, r.Aps, r.Aes, r.Bps, r.Bes}) cudaFree(p);
         if (r.filled) cudaEventDestroy(r.filled);
-        if (r.copied) cudaEventDestroy(r.copied);
         r = Ring{};
     }
 };
@@ -611,7 +608,6 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
             CU(cudaMalloc(&r.Aes, sizeof(double) * c->nE * cap));
         }
         CU(cudaEventCreateWithFlags(&r.filled, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&r.copied, cudaEventDisableTiming));
     }
     c->ring_cap = cap; c->ring_keep = keep_par;
     return SIGNER_OK;
@@ -698,7 +694,6 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->key = Key{(uint32_t)o->seed, (uint32_t)(o->seed >> 32)};
     c->sweep0 = o->sweep0; c->Pfixed = o->Pfixed ? 1 : 0;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->ll_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ll_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ll_done, cudaEventDisableTiming));
@@ -870,7 +865,6 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     c->last_eval = eval;
     if (out && eval > 0) {
         CU(cudaStreamSynchronize(c->stream));
-        CU(cudaStreamSynchronize(c->copy_stream));
         ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1]));
         join_faulters();
         if (zcube && out->Zs) {
@@ -1273,7 +1267,6 @@ int signer_chain_sync(signer_chain *c)
     if (!c) return fail(SIGNER_ERR_ARG, "null chain");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaStreamSynchronize(c->copy_stream));
     return SIGNER_OK;
 }
 

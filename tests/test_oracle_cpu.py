@@ -2,6 +2,7 @@
 known answers, the deterministic math against libm/scipy, the samplers against exact laws, and the
 invariants of the model.  'Parity unpinned' (no upstream vectors exist): these are what pins it."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -204,3 +205,17 @@ def test_host_mirror_pieces_cpu(sg):
     assert sg.Optimal_sigs(tf, 2, 10, 2)[0] == 5 and sg.Optimal_sigs(tf, 2, 40, 8)[0] == 5
     flat = lambda n: [np.zeros(9), None]
     assert sg.Optimal_sigs(flat, 2, 10, 2)[0] == 2
+
+
+def test_det_tables_are_the_generators_output_and_identical_on_both_sides(tmp_path):
+    """det_tables.h (log table, ziggurat layers): the oracle's and the CUDA library's copies are byte-identical and
+    equal to what scripts/make_det_tables.py writes"""
+    import filecmp, shutil, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a, b = os.path.join(root, "oracle", "det_tables.h"), os.path.join(root, "signer_b200", "csrc", "det_tables.h")
+    assert filecmp.cmp(a, b, shallow=False)
+    work = tmp_path / "repo"
+    (work / "scripts").mkdir(parents=True); (work / "oracle").mkdir(); (work / "signer_b200" / "csrc").mkdir(parents=True)
+    shutil.copy(os.path.join(root, "scripts", "make_det_tables.py"), work / "scripts" / "make_det_tables.py")
+    subprocess.check_call([sys.executable, str(work / "scripts" / "make_det_tables.py")], stdout=subprocess.DEVNULL)
+    assert filecmp.cmp(a, str(work / "oracle" / "det_tables.h"), shallow=False)
