@@ -594,7 +594,12 @@ int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slo
 int ensure_rings(signer_chain *c, int eval, int keep_par)
 {
     const size_t per_sweep = sizeof(double) * (c->nP + c->nE) * (keep_par ? 3 : 2);
-    int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)eval, kRingBytes / per_sweep));
+    size_t ring_bytes = kRingBytes;
+    if (const char *e = std::getenv("SIGNER_RING_BYTES")) {     // tests: force many small chunks through the copy-out path
+        const long long v = std::atoll(e);
+        if (v > 0) ring_bytes = (size_t)v;
+    }
+    int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes / per_sweep));
     if (c->ring_cap >= cap && c->ring_keep >= keep_par) return SIGNER_OK;
     for (int b = 0; b < 2; ++b) {
         signer_chain::free_ring(c->ring[b]);

@@ -98,3 +98,16 @@ def test_chain_on_a_torch_stream(sg):
         b = c.run(burn=20, eval=0).state
     for k in a:
         assert np.array_equal(a[k], b[k])
+
+
+def test_many_ring_chunks_are_bit_exact(sg, oracle, monkeypatch):
+    """the samples leave the device ring in chunks through the copy-out pool while the chain keeps running: with a ring of
+    two sweeps per set (15 and 7 chunks, both sets reused many times) every sample cube still equals the oracle's"""
+    M, W, st = small_problem(I=40, J=300, K=6, seed=11)
+    slice_bytes = 8 * (40 * 6 + 6 * 300)                            # one P-family + one E-family matrix
+    monkeypatch.setenv("SIGNER_RING_BYTES", str(2 * 3 * slice_bytes))        # keep_par: three slices per sweep
+    got, want = run_both(sg, oracle, M, W, st, 6, burn=4, eval=29, keep_par=True, seed=2211)
+    compare_all(got, want)
+    monkeypatch.setenv("SIGNER_RING_BYTES", str(2 * 2 * slice_bytes))        # keep_par=FALSE: two slices per sweep
+    got, want = run_both(sg, oracle, M, W, st, 6, burn=2, eval=13, keep_par=False, seed=2212)
+    compare_all(got, want, keep_par=False)
