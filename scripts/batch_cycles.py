@@ -34,7 +34,7 @@ for lo, hi in [(0, 10), (10, 100), (100, 300), (300, 1000), (1000, 2000), (2000,
 ph = np.zeros((2, 8), dtype=np.uint64)
 L.signer_debug_z_phases.argtypes = [C.c_void_p]
 assert L.signer_debug_z_phases(ph.ctypes.data_as(C.c_void_p)) == 0
-names = ["cells+claim", "staging", "direct loop", "sort", "chain", "tail", "flush+emit", "-"]
+names = ["cells+claim", "staging", "direct loop", "sort", "chain", "tail", "degenerate", "-"]
 tot = ph.sum()
 for c, cname in enumerate(["small batches", "large batches"]):
     print(cname, " ".join("%s %.1f%%" % (names[i], 100.0 * ph[c, i] / tot) for i in range(7)), " | class total %.1f%%" % (100.0 * ph[c].sum() / tot))

@@ -153,7 +153,8 @@ SG_D void z_direct(const double *buf, const UStream &us, int ng, int nn, int tma
 
 // the direct draws that finish the chains of one batch, shared by the warp: the cells' Philox blocks (four draws
 // each) are dealt round-robin to the lanes, whoever owns the cell -- a lane reads the owner's column of shared
-// memory and adds to the owner's count bytes.  incl/excl: running totals of the lanes' block counts.
+// memory and adds the draws to the statistics under the owner's row and column.  incl/excl: running totals of
+// the lanes' block counts.
 template <int NG>
 SG_D void z_tail(const double *buf, const ZParams &p, int *zin_s, int lane, int ng, int incl, int excl, int utot, int nrem,
                  double Sr, int row, int col)
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                 }
             }
             SG_ZCLK(3)                                      // sort
-            // conditional binomials in visiting order while more than kNDirect mutations are left;
+            // conditional binomials in visiting order while more than kNTail mutations are left;
             // binomial t uses word t&3 of block t>>2
             double rem = S;
             int tl = 0;                                                        // classes this lane has visited
@@ -366,8 +367,8 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
             // cumulative sums in index order with the visited classes zeroed; draw d of a cell uses word d&3 of
             // block kTailBlock0 + (d>>2) of the cell's stream and the same search as the small counts.  The warp
             // shares this work: the cells' Philox blocks (four draws each) are dealt round-robin to the lanes,
-            // whoever owns the cell -- a lane reads the owner's column of shared memory and adds to the owner's
-            // count bytes.
+            // whoever owns the cell -- a lane reads the owner's column of shared memory and adds the draws to the
+            // statistics under the owner's context and genome.
             if (__any_sync(kFull, nrem > 0)) {
                 double Sr = 0.0;
                 if (nrem > 0) {
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
 
         SG_ZCLK(5)                                          // tail
         if (nlast) z_emit(p, zin_s, row, col, K - 1, nlast);                    // degenerate probabilities
-        SG_ZCLK(6)                                          // flush + emits
+        SG_ZCLK(6)                                          // degenerate cells
 #ifdef SG_Z_TIMING
         if (lane == 0 && t_batch < (1 << 16)) g_z_batch_cycles[t_batch] = (unsigned)(clock64() - t_begin);
 #endif
