@@ -28,6 +28,8 @@ extern "C" {
 #endif
 
 #define SIGNER_ABI_VERSION 2
+/* Version of the draw specification: the same seed gives the same chain only within one version. */
+#define SIGNER_DRAW_SPEC_VERSION 6
 
 /* status codes */
 enum {
@@ -181,6 +183,7 @@ const char *signer_last_error(void);
  * first sweep's launch to the last result on the host, excluding upload and set-up. */
 double signer_last_loop_ms(void);
 int signer_version(void);
+int signer_draw_spec_version(void);
 /* Number of CUDA devices visible, or a negative status. */
 int signer_device_count(void);
 

@@ -57,7 +57,7 @@ EXPORTS = [
     "signer_chain_run", "signer_chain_sync", "signer_chain_fetch_state", "signer_chain_fetch_stats",
     "signer_chain_profile", "signer_chain_sweeps", "signer_chain_launches", "signer_chain_draw_counts", "signer_draw_ceiling", "signer_chain_destroy", "signer_gibbs_batch",
     "signer_test_math", "signer_test_binomial", "signer_test_gamma", "signer_test_perm",
-    "signer_test_philox", "signer_last_error", "signer_last_loop_ms", "signer_version", "signer_device_count",
+    "signer_test_philox", "signer_last_error", "signer_last_loop_ms", "signer_version", "signer_draw_spec_version", "signer_device_count",
 ]
 
 _LIB = None
@@ -120,6 +120,7 @@ def lib():
     L.signer_last_loop_ms.restype = C.c_double
     L.signer_last_loop_ms.argtypes = []
     L.signer_version.restype = C.c_int
+    L.signer_draw_spec_version.restype = C.c_int
     L.signer_device_count.restype = C.c_int
     _LIB = L
     return L

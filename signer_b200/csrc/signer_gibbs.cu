@@ -1224,6 +1224,7 @@ extern "C" {
 const char *signer_last_error(void) { return g_err.c_str(); }
 double signer_last_loop_ms(void) { return g_loop_ms; }
 int signer_version(void) { return SIGNER_ABI_VERSION; }
+int signer_draw_spec_version(void) { return SIGNER_DRAW_SPEC_VERSION; }
 
 int signer_device_count(void)
 {
