@@ -395,8 +395,9 @@ def main():
         del zrun
         nb = max(1, args.steps // 2)
         ne = max(1, args.steps - nb)
-        sg.GibbsSamplerCpp(M, W, Z0, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *hyper, 3, 3,
-                           False, False, False, False, False, seed=6, device=local)      # warm-up of the call path
+        wb = max(3, args.warmup // 2)
+        sg.GibbsSamplerCpp(M, W, Z0, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *hyper, wb, max(3, args.warmup - wb),
+                           False, False, False, False, False, seed=6, device=local)      # the W warm-up sweeps through the same call
         # three full calls, the median reported (all three kept in `seconds_all`): the call returns ~3 GB of freshly
         # allocated host pages, whose first-touch cost varies from call to call on the same box
         dts = []
