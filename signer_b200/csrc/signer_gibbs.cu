@@ -16,6 +16,7 @@
 #include <deque>
 #include <cstring>
 #include <dlfcn.h>
+#include <sys/mman.h>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -72,6 +73,7 @@ struct DeviceData {
 
 // cells per batch of z_alloc_fused's work list for cells of count n (see upload_data); SIGNER_Z_WIDTHS="n:w,n:w,..."
 // (descending n) overrides the built-in grading for experiments
+const bool g_no_hugepage = [] { const char *e = std::getenv("SIGNER_KEEP_HUGEPAGES"); return !(e && e[0] == '1'); }();
 const bool g_sort_rounds = [] { const char *e = std::getenv("SIGNER_Z_SORT_EXACT"); return !(e && e[0] == '1'); }();
 
 int batch_width(int n)
@@ -510,6 +512,15 @@ void prefault(double *p, size_t n_doubles)
     if (!p) return;
     volatile char *b = reinterpret_cast<volatile char *>(p);
     const size_t bytes = n_doubles * sizeof(double);
+    if (g_no_hugepage) {
+        // A caller that asked for transparent huge pages (NumPy does for large arrays) makes every first touch wait
+        // for a free 2 MB block -- direct compaction inside the fault, measured as sporadic stalls of up to a second
+        // per call.  These pages are written once and read once: plain 4 KB faults, spread over the helper threads,
+        // are faster and predictable.  (A hint only; R's vectors are not huge-page backed in the first place.)
+        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(p) + 4095) & ~uintptr_t(4095);
+        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(p) + bytes) & ~uintptr_t(4095);
+        if (a1 > a0) madvise(reinterpret_cast<void *>(a0), a1 - a0, MADV_NOHUGEPAGE);
+    }
     for (size_t off = 0; off < bytes; off += 4096) b[off] = 0;
     if (bytes) b[bytes - 1] = 0;
 }
