@@ -188,6 +188,67 @@ def test_conjugate_step_moments(oracle):
     assert abs(zs.mean()) < 5 / math.sqrt(zs.size) and abs(zs.var() - 1) < 0.05
 
 
+def _prior_draws(rng, n, I, J, K, h):
+    """theta ~ prior of the model (R/cpp_eBayesNMF.R:40-50)"""
+    Ap = rng.exponential(1 / h["lp"], size=(n, I, K)); Bp = rng.gamma(h["ap"], 1 / h["bp"], size=(n, I, K))
+    Ae = rng.exponential(1 / h["le"], size=(n, K, J)); Be = rng.gamma(h["ae"], 1 / h["be"], size=(n, K, J))
+    return dict(P=rng.gamma(Ap + 1, 1 / Bp), E=rng.gamma(Ae + 1, 1 / Be), Ap=Ap, Bp=Bp, Ae=Ae, Be=Be)
+
+
+def test_sweep_leaves_the_joint_distribution_invariant(oracle):
+    """Exact-invariance test of the WHOLE random-scan sweep (all seven steps, the latent allocation included), in the
+    spirit of Geweke (2004): theta ~ prior, M ~ p(M | theta), then a few sweeps given M.  If every step leaves its
+    conditional invariant, theta afterwards is again a draw from the prior -- independent replications, so the
+    two-sample KS tests against fresh prior draws are exact.  (A 15 % error in one hyper-parameter of the sampler
+    drives these p-values below 1e-9.)"""
+    I, J, K, R = 2, 3, 2, 8000
+    h = dict(ap=3.0, bp=2.0, ae=3.0, be=2.0, lp=2.0, le=2.0, var_ap=0.5, var_ae=0.5)
+    rng = np.random.default_rng(11)
+    W = np.asfortranarray(rng.uniform(0.5, 1.5, size=(I, J)))
+    th = _prior_draws(rng, R, I, J, K, h)
+    after = {k: np.empty_like(v) for k, v in th.items()}
+    for r in range(R):
+        st = {k: np.asfortranarray(v[r]) for k, v in th.items()}
+        M = rng.poisson((st["P"] @ st["E"]) * W).astype(np.float64)
+        out = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], hyper=h, burn=3, eval=0,
+                               seed=11000003 + r, want_Z=False)
+        for k in after:
+            after[k][r] = out[k]
+    ref = _prior_draws(rng, 4 * R, I, J, K, h)
+    pvals = {}
+    for k in th:
+        a, q = after[k].reshape(R, -1), ref[k].reshape(4 * R, -1)
+        pvals[k] = min(stats.ks_2samp(a[:, c], q[:, c]).pvalue for c in range(a.shape[1]))
+    lam_a = np.einsum("rik,rkj->rij", after["P"], after["E"]).reshape(R, -1)          # a functional that couples the families
+    lam_q = np.einsum("rik,rkj->rij", ref["P"], ref["E"]).reshape(4 * R, -1)
+    pvals["PE"] = min(stats.ks_2samp(lam_a[:, c], lam_q[:, c]).pvalue for c in range(lam_a.shape[1]))
+    assert min(pvals.values()) > 1e-4, pvals
+    assert (after["Ap"] != th["Ap"]).mean() > 0.3 and (after["P"] != th["P"]).all()       # the chain did move
+
+
+@pytest.mark.parametrize("step", [6, 7])
+def test_mh_step_is_stationary_for_its_conditional(oracle, step):
+    """Steps 6/7 (src/gibbs_2.cpp:172-251) on one element: the target is p(A | X, B) ~ exp(-l A) (B X)^A / Gamma(A+1).
+    Start from exact draws of it (inverse cdf on a fine grid), apply three MH steps, compare with the exact cdf."""
+    x, b, l, var, R = 0.37, 2.3, 1.7, 0.6, 6000
+    grid = np.linspace(0.0, 14.0, 280001)[1:]
+    dens = np.exp(grid * (math.log(b * x) - l) - special.gammaln(grid + 1))
+    cdf = np.cumsum(dens); cdf /= cdf[-1]
+    rng = np.random.default_rng(step)
+    a0 = np.interp(rng.uniform(size=R), cdf, grid)
+    hyper = dict(lp=l, le=l, var_ap=var, var_ae=var)
+    M, W, one = np.array([[3.0]]), np.array([[1.0]]), np.ones((1, 1))
+    out = np.empty(R)
+    for r in range(R):
+        A = np.array([[a0[r]]])
+        st = dict(P=x * one, E=2 * one, Ap=A, Bp=b * one, Ae=one, Be=one) if step == 6 else dict(P=2 * one, E=x * one, Ap=one, Bp=one, Ae=A, Be=b * one)
+        res = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], hyper=hyper, burn=3, eval=0,
+                               seed=77000 + r, forced_order=[[step, 0, 0, 0, 0, 0, 0]] * 3, want_Z=False)
+        out[r] = res["Ap" if step == 6 else "Ae"][0, 0]
+    assert (out != a0).mean() > 0.3                                    # proposals are accepted
+    assert stats.kstest(out, lambda t: np.interp(t, grid, cdf)).pvalue > 1e-3
+
+
 def test_host_mirror_pieces_cpu(sg):
     from signer_b200.signexp import SignExp, _fivenum_whiskers
     from signer_b200.estimate import EstimateParameters
