@@ -195,25 +195,29 @@ def _prior_draws(rng, n, I, J, K, h):
     return dict(P=rng.gamma(Ap + 1, 1 / Bp), E=rng.gamma(Ae + 1, 1 / Be), Ap=Ap, Bp=Bp, Ae=Ae, Be=Be)
 
 
-def test_sweep_leaves_the_joint_distribution_invariant(oracle):
+@pytest.mark.parametrize("be", [2.0, 40.0])        # 40: exposures ~ 20, most counts above 32 (chain + remainder path of step 1)
+def test_sweep_leaves_the_joint_distribution_invariant(oracle, be):
     """Exact-invariance test of the WHOLE random-scan sweep (all seven steps, the latent allocation included), in the
     spirit of Geweke (2004): theta ~ prior, M ~ p(M | theta), then a few sweeps given M.  If every step leaves its
     conditional invariant, theta afterwards is again a draw from the prior -- independent replications, so the
     two-sample KS tests against fresh prior draws are exact.  (A 15 % error in one hyper-parameter of the sampler
     drives these p-values below 1e-9.)"""
     I, J, K, R = 2, 3, 2, 8000
-    h = dict(ap=3.0, bp=2.0, ae=3.0, be=2.0, lp=2.0, le=2.0, var_ap=0.5, var_ae=0.5)
+    h = dict(ap=3.0, bp=2.0, ae=3.0, be=be, lp=2.0, le=2.0, var_ap=0.5, var_ae=0.5)
     rng = np.random.default_rng(11)
     W = np.asfortranarray(rng.uniform(0.5, 1.5, size=(I, J)))
     th = _prior_draws(rng, R, I, J, K, h)
+    big = 0
     after = {k: np.empty_like(v) for k, v in th.items()}
     for r in range(R):
         st = {k: np.asfortranarray(v[r]) for k, v in th.items()}
         M = rng.poisson((st["P"] @ st["E"]) * W).astype(np.float64)
+        big += int((M > 32).sum())
         out = oracle.gibbs_run(M, W, None, st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], hyper=h, burn=3, eval=0,
                                seed=11000003 + r, want_Z=False)
         for k in after:
             after[k][r] = out[k]
+    assert be < 10 or big > R                                          # the large-count path was exercised
     ref = _prior_draws(rng, 4 * R, I, J, K, h)
     pvals = {}
     for k in th:
