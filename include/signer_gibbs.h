@@ -12,8 +12,13 @@
  *     M, W   I x J        P, Ap, Bp  I x K        E, Ae, Be  K x J
  *     Z cube I x J x K    element (s,g,m) at s + I*(g + J*m)
  *     sample cubes (i,n,r) / (n,j,r): slice r is one full matrix   (src/gibbs_2.cpp:289-302)
- * Inputs are never written.  Outputs are caller-allocated; the library keeps nothing after a
- * stateless call returns.  No torch types, no R API, never exit()/abort().
+ * Inputs are never written.  Outputs are caller-allocated; nothing the library keeps after a
+ * stateless call returns refers to caller memory.  What it does keep, per process, is reusable device
+ * state: the device copy of the last few cohorts (M, W: layouts and work list, keyed by a 128-bit hash
+ * of their content -- the EM loop and the model selection call the sampler again and again on the same
+ * matrices, R/cpp_eBayesNMF.R:97-157, R/Optimal_sigs.R:27), the stream-ordered memory pool and pinned
+ * staging buffers.  signer_release_caches() gives all of it back.  No torch types, no R API, never
+ * exit()/abort().
  *
  * There is NO CPU fallback: every entry that computes needs a CUDA device and returns
  * SIGNER_ERR_CUDA without one.
@@ -27,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SIGNER_ABI_VERSION 2
+#define SIGNER_ABI_VERSION 3
 /* Version of the draw specification: the same seed gives the same chain only within one version. */
 #define SIGNER_DRAW_SPEC_VERSION 6
 
@@ -104,7 +109,7 @@ int signer_chain_create(const signer_problem *problem, const signer_state *state
                         const signer_opts *opts, signer_chain **chain);
 /* Launch on an existing CUDA stream (a cudaStream_t) instead of the chain's own; pass NULL to
  * restore (so the legacy default stream, whose handle is NULL, cannot be selected).  Lets a host
- * framework time the chain with its own events. */
+ * framework time the chain with its own events.  The stream must outlive the chain (or be restored first). */
 int signer_chain_set_stream(signer_chain *chain, void *cuda_stream);
 /* Update the hyper-hyperparameters between EM iterations (ap,bp,ae,be,lp,le,var_ap,var_ae). */
 int signer_chain_set_hyper(signer_chain *chain, const double hyper[8]);
@@ -176,6 +181,10 @@ void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 /* Measured ceiling of the uniform-draw rate on `device`: a kernel that only generates Philox4x32-10
  * blocks, turns each into four 32-bit uniforms and does one inversion step per uniform, no memory traffic. */
 int signer_draw_ceiling(int32_t device, double *draws_per_s);
+
+/* Drop the cached cohorts, trim the device memory pools and free the cached pinned buffers (see the header comment).
+ * Environment: SIGNER_COHORT_CACHE_MB (default 16384; 0 disables the cohort cache). */
+void signer_release_caches(void);
 
 /* Thread-local text of the last error on this thread ("" if none). */
 const char *signer_last_error(void);

@@ -57,7 +57,7 @@ EXPORTS = [
     "signer_chain_run", "signer_chain_sync", "signer_chain_fetch_state", "signer_chain_fetch_stats",
     "signer_chain_profile", "signer_chain_sweeps", "signer_chain_launches", "signer_chain_draw_counts", "signer_draw_ceiling", "signer_chain_destroy", "signer_gibbs_batch",
     "signer_test_math", "signer_test_binomial", "signer_test_gamma", "signer_test_perm",
-    "signer_test_philox", "signer_last_error", "signer_last_loop_ms", "signer_version", "signer_draw_spec_version", "signer_device_count",
+    "signer_test_philox", "signer_release_caches", "signer_last_error", "signer_last_loop_ms", "signer_version", "signer_draw_spec_version", "signer_device_count",
 ]
 
 _LIB = None
@@ -115,6 +115,8 @@ def lib():
     L.signer_test_perm.argtypes = [C.c_uint64, C.c_uint32, ip]
     L.signer_test_philox.restype = None
     L.signer_test_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.signer_release_caches.restype = None
+    L.signer_release_caches.argtypes = []
     L.signer_last_error.restype = C.c_char_p
     L.signer_last_error.argtypes = []
     L.signer_last_loop_ms.restype = C.c_double

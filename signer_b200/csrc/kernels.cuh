@@ -844,19 +844,40 @@ __global__ void __launch_bounds__(1024) tree_sum(double *a, int n2, const double
 }
 
 // ------------------------------------------------------------------------------------------------
-// entry: reduce one slab Z[:,:,k] of the reference's cube to its sums (src/gibbs_2.cpp:112,129)
+// entry: reduce one piece of the reference's cube -- columns [ja, ja+nj) of slice k, column-major I x nj -- to its
+// sums (the only use the sampler makes of its Z argument, src/gibbs_2.cpp:112,129).  One warp per column: coalesced
+// reads along the contexts; the context sums go through a block-wide shared-memory accumulator when I fits.
 // ------------------------------------------------------------------------------------------------
-__global__ void zslab_reduce(const double *slab, int I, int J, int K, int k, int *Zin, int *Znj)
+__global__ void zslab_reduce(const double *piece, int I, int nj, int ja, int K, int k, int use_smem, int *Zin, int *Znj)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
-    int colsum = 0;
-    for (int i = 0; i < I; ++i) {
-        const int z = (int)slab[(size_t)i + (size_t)I * j];
-        colsum += z;
-        if (z) atomicAdd(Zin + (size_t)i + (size_t)I * k, z);
+    extern __shared__ int zin_blk[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < I; i += blockDim.x) zin_blk[i] = 0;
+        __syncthreads();
     }
-    Znj[(size_t)k + (size_t)K * j] = colsum;
+    const int jb0 = blockIdx.x * 64, jb1 = min(nj, jb0 + 64);
+    for (int jl = jb0 + warp; jl < jb1; jl += nw) {
+        const double *col = piece + (size_t)I * jl;
+        int colsum = 0;
+        for (int i = lane; i < I; i += 32) {
+            const int z = (int)col[i];
+            colsum += z;
+            if (z) {
+                if (use_smem) atomicAdd(zin_blk + i, z);
+                else atomicAdd(Zin + (size_t)i + (size_t)I * k, z);
+            }
+        }
+        colsum = __reduce_add_sync(kFull, colsum);
+        if (lane == 0) Znj[(size_t)k + (size_t)K * (ja + jl)] = colsum;
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < I; i += blockDim.x) {
+            const int v = zin_blk[i];
+            if (v) atomicAdd(Zin + (size_t)i + (size_t)I * k, v);
+        }
+    }
 }
 
 // sufficient statistics of stored samples for the EM M-step (R/EstimateParameters.R:1-13):

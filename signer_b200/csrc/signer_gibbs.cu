@@ -5,18 +5,17 @@
 // random scan (:303-318), sample storage (:320-334) and the returned list (:406-423).
 // There is no CPU path in this file: every entry point that computes launches CUDA kernels.
 #include "../../include/signer_gibbs.h"
+#include "cohort.hpp"
+#include "host_util.hpp"
 #include "kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
-#include <chrono>
-#include <condition_variable>
-#include <deque>
 #include <cstring>
 #include <dlfcn.h>
-#include <sys/mman.h>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -25,176 +24,24 @@
 #include <vector>
 
 using namespace sg;
+using sgh::DeviceData;
+using sgh::DevTemp;
+using sgh::GroupPtr;
+using sgh::PinnedBuf;
+using sgh::TransferPool;
+using sgh::dalloc;
+using sgh::dfree;
+using sgh::fail;
+using sgh::g_err;
 
 namespace {
 
-thread_local std::string g_err;
 thread_local double g_loop_ms = 0.0;      // wall time of the last sweep loop on this thread (sharded / stateless runs)
-
-int fail(int code, const std::string &msg)
-{
-    g_err = msg;
-    return code;
-}
-
-#define CU(call)                                                                                      \
-    do {                                                                                              \
-        cudaError_t e_ = (call);                                                                      \
-        if (e_ != cudaSuccess)                                                                        \
-            return fail(e_ == cudaErrorMemoryAllocation ? SIGNER_ERR_NOMEM : SIGNER_ERR_CUDA,         \
-                        std::string(#call) + ": " + cudaGetErrorString(e_));                          \
-    } while (0)
-
-#define ST(call)                                  \
-    do {                                          \
-        int s_ = (call);                          \
-        if (s_ != SIGNER_OK) return s_;           \
-    } while (0)
 
 constexpr size_t kRingBytes = size_t(256) << 20;   // per ring set (two sets): small enough to pipeline D2H behind compute
 
-// The data of one cohort on one device, shared by every chain on that device.
-struct DeviceData {
-    int device = 0, I = 0, J = 0, Jp = 0, n2 = 0;
-    int col0 = 0, Jglobal = 0;  // column shard: first global genome, genomes in the whole cohort
-    // z_alloc's work list: the non-zero cells sorted by count (largest first, ties genome-major)
-    unsigned short *cell_row = nullptr;
-    int *cell_col = nullptr, *cell_n = nullptr;
-    int n_cells = 0;
-    int *Mrow = nullptr;       // [I][Jp], original genome order (log-likelihood)
-    double *W = nullptr;       // [I][Jp]
-    double *lgm = nullptr;     // sum lgamma(M+1), one double
-    ~DeviceData()
-    {
-        cudaSetDevice(device);
-        cudaFree(cell_row); cudaFree(cell_col); cudaFree(cell_n); cudaFree(Mrow); cudaFree(W); cudaFree(lgm);
-    }
-};
-
-// cells per batch of z_alloc_fused's work list for cells of count n (see upload_data); SIGNER_Z_WIDTHS="n:w,n:w,..."
-// (descending n) overrides the built-in grading for experiments
-const bool g_no_hugepage = [] { const char *e = std::getenv("SIGNER_KEEP_HUGEPAGES"); return !(e && e[0] == '1'); }();
-const bool g_sort_rounds = [] { const char *e = std::getenv("SIGNER_Z_SORT_EXACT"); return !(e && e[0] == '1'); }();
-
-int batch_width(int n)
-{
-    static const std::vector<std::pair<int, int>> grade = [] {
-        std::vector<std::pair<int, int>> g;
-        if (const char *e = std::getenv("SIGNER_Z_WIDTHS")) {
-            g.clear();
-            int a = 0, b = 0, used = 0;
-            while (std::sscanf(e, "%d:%d%n", &a, &b, &used) == 2) {
-                g.emplace_back(a, std::max(1, std::min(32, b)));
-                e += used;
-                if (*e == ',') ++e;
-            }
-        }
-        return g;
-    }();
-    for (const auto &g : grade) if (n >= g.first) return g.second;
-    return 32;
-}
-
-int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out, int col0 = 0,
-                int Jglobal = -1)
-{
-    if (Jglobal < 0) Jglobal = J;
-    if (I <= 0 || J <= 0 || !M || !W) return fail(SIGNER_ERR_ARG, "problem: I, J must be positive and M, W non-null");
-    if ((long long)I * J >= (1LL << 31)) return fail(SIGNER_ERR_ARG, "problem: I*J must be below 2^31");
-    CU(cudaSetDevice(device));
-    auto d = std::make_shared<DeviceData>();
-    d->device = device; d->I = I; d->J = J; d->Jp = (J + 31) / 32 * 32;
-    d->col0 = col0; d->Jglobal = Jglobal;
-    d->n2 = 1; while (d->n2 < Jglobal) d->n2 <<= 1;
-    if (I > 65535) return fail(SIGNER_ERR_ARG, "problem: I must be below 65536");
-    const size_t n = (size_t)I * d->Jp;
-    std::vector<int> m(n, 0);
-    std::vector<double> w(n, 0.0);
-    std::vector<int> cells;                  // element ids i + I*j of the non-zero cells, genome-major
-    for (int j = 0; j < J; ++j)
-        for (int i = 0; i < I; ++i) {
-            const double mv = M[(size_t)i + (size_t)I * j], wv = W[(size_t)i + (size_t)I * j];
-            if (!(mv >= 0.0) || !(mv <= 2147483647.0)) return fail(SIGNER_ERR_NONFINITE, "M has a negative, non-finite or too large entry");
-            if (!(wv >= 0.0) || !(wv <= 1.7976931348623157e308)) return fail(SIGNER_ERR_NONFINITE, "W has a negative or non-finite entry");
-            const int mi = (int)mv;                      // int size (src/gibbs_2.cpp:31)
-            m[(size_t)i * d->Jp + j] = mi;
-            w[(size_t)i * d->Jp + j] = wv;
-            if (mi > 0) cells.push_back(i + I * j);
-        }
-    // z_alloc_fused's work list (a private order: results do not depend on it): the non-zero cells sorted by
-    // count, largest first (ties keep the genome-major order), cut into batches of 32 list entries = one warp
-    // round each.  batch_width() can give the heaviest cells narrower batches (the rest of the batch is padding,
-    // count 0); measured on B200 every such grading lost to plain 32-cell batches, so the default is none.
-    std::vector<unsigned short> crow;
-    std::vector<int> ccol, cn;
-    {
-        const size_t nz = cells.size();
-        std::vector<int> cnt(nz);
-        for (size_t t = 0; t < nz; ++t) {
-            const int i = cells[t] % I, j = cells[t] / I;
-            cnt[t] = m[(size_t)i * d->Jp + j];
-        }
-        // sort key: counts above kNDirect by value; smaller ones by their number of direct-method rounds (four
-        // draws per Philox block), so that cells that cost the same stay in genome-major order and a warp's lanes
-        // read few distinct columns of E.  Counting sort (stable) when the keys are small enough.
-        auto key = [&](size_t t) { return cnt[t] > kNDirect ? cnt[t] : (g_sort_rounds ? 4 * ((cnt[t] + 3) / 4) : cnt[t]); };
-        std::vector<size_t> idx(nz);
-        int kmax = 0;
-        for (size_t t = 0; t < nz; ++t) kmax = std::max(kmax, key(t));
-        if (kmax <= (1 << 22)) {
-            std::vector<size_t> pos((size_t)kmax + 2, 0);
-            for (size_t t = 0; t < nz; ++t) pos[(size_t)key(t)]++;
-            size_t run = 0;
-            for (int v = kmax; v >= 0; --v) { const size_t h = pos[(size_t)v]; pos[(size_t)v] = run; run += h; }
-            for (size_t t = 0; t < nz; ++t) idx[pos[(size_t)key(t)]++] = t;
-        } else {
-            for (size_t t = 0; t < nz; ++t) idx[t] = t;
-            std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return key(a) > key(b); });
-        }
-        crow.reserve(nz + 4096); ccol.reserve(nz + 4096); cn.reserve(nz + 4096);
-        size_t t = 0;
-        while (t < nz) {
-            const int width = batch_width(cnt[idx[t]]);
-            int filled = 0;
-            for (; filled < width && t < nz; ++filled, ++t) {
-                const size_t e = idx[t];
-                crow.push_back((unsigned short)(cells[e] % I)); ccol.push_back(cells[e] / I); cn.push_back(cnt[e]);
-            }
-            if (t < nz) for (; filled < 32; ++filled) { crow.push_back(0); ccol.push_back(0); cn.push_back(0); }
-        }
-    }
-    d->n_cells = (int)cn.size();
-    if (cn.empty()) { crow.push_back(0); ccol.push_back(0); cn.push_back(0); }
-    const size_t nc = cn.size();
-    CU(cudaMalloc(&d->cell_row, nc * sizeof(unsigned short)));
-    CU(cudaMalloc(&d->cell_col, nc * sizeof(int)));
-    CU(cudaMalloc(&d->cell_n, nc * sizeof(int)));
-    CU(cudaMalloc(&d->Mrow, n * sizeof(int)));
-    CU(cudaMalloc(&d->W, n * sizeof(double)));
-    CU(cudaMalloc(&d->lgm, sizeof(double)));
-    CU(cudaMemcpy(d->cell_row, crow.data(), nc * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d->cell_col, ccol.data(), nc * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d->cell_n, cn.data(), nc * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d->Mrow, m.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d->W, w.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-    // constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180); a column shard computes it with its peers
-    if (Jglobal == J) {
-        double *col = nullptr;
-        CU(cudaMalloc(&col, (size_t)d->n2 * sizeof(double)));
-        CU(cudaMemset(col, 0, (size_t)d->n2 * sizeof(double)));
-        LLParams lp{I, J, d->Jp, 1, d->Mrow, d->W, nullptr, nullptr, col, 1, nullptr, 0, nullptr, nullptr, nullptr};
-        loglik_cols<<<(J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(1)>>>(lp);
-        tree_sum<<<1, 1024>>>(col, d->n2, nullptr, d->lgm);
-        CU(cudaGetLastError());
-        CU(cudaDeviceSynchronize());
-        CU(cudaFree(col));
-    }
-    out = d;
-    return SIGNER_OK;
-}
-
-// z_alloc_fused may need more than 48 KB of dynamic shared memory; raise the limit once per device to the
-// architectural maximum so that concurrent chains with different K never race on the attribute.
+// z_alloc_fused and loglik_cols may need more than 48 KB of dynamic shared memory; raise the limits once per device to
+// the architectural maximum so that concurrent chains with different K never race on the attribute.
 int g_z_dyn_smem_max[64] = {0};
 
 int ensure_device_setup(int device)
@@ -205,12 +52,15 @@ int ensure_device_setup(int device)
     if (device < 0 || device >= 64) return fail(SIGNER_ERR_ARG, "device ordinal out of range");
     if (done[device]) return SIGNER_OK;
     CU(cudaSetDevice(device));
+    ST(sgh::ensure_pool(device));
     int optin = 0;
     CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, z_alloc_fused));
     g_z_dyn_smem_max[device] = optin - (int)fa.sharedSizeBytes;
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
+    CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (33 K + 3264) bytes: above 48 KB from K = 88 (K <= 128 is accepted)
+    CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
 #ifdef SG_Z_CARVEOUT
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, SG_Z_CARVEOUT));
 #endif
@@ -218,88 +68,39 @@ int ensure_device_setup(int device)
     return SIGNER_OK;
 }
 
+// constant of the data: sum lgamma(M+1) (lgM in R/cpp_eBayesNMF.R:180), once per cohort; a column shard computes it
+// with its peers (sharded_run)
+std::mutex g_lgm_mu;
+int ensure_lgm(DeviceData &d)
+{
+    std::lock_guard<std::mutex> lk(g_lgm_mu);
+    if (d.lgm_ready || d.Jglobal != d.J) return SIGNER_OK;
+    CU(cudaSetDevice(d.device));
+    ST(ensure_device_setup(d.device));
+    DevTemp col;
+    ST(col.get((size_t)d.n2 * sizeof(double), nullptr));
+    CU(cudaMemsetAsync(col.p, 0, (size_t)d.n2 * sizeof(double), nullptr));
+    LLParams lp{d.I, d.J, d.Jp, 1, d.Mrow, d.W, nullptr, nullptr, col.as<double>(), 1, nullptr, 0, nullptr, nullptr, nullptr};
+    loglik_cols<<<(d.J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(1)>>>(lp);
+    tree_sum<<<1, 1024>>>(col.as<double>(), d.n2, nullptr, d.lgm);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(nullptr));
+    d.lgm_ready = true;
+    return SIGNER_OK;
+}
+
+int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out, int col0 = 0,
+                int Jglobal = -1)
+{
+    static_assert(kNDirect == 32, "cohort.cu sorts the work list with the same threshold (kListDirect)");
+    ST(sgh::get_cohort(device, I, J, M, W, col0, Jglobal, out));
+    return ensure_lgm(*out);
+}
+
 struct Ring {
     double *Ps = nullptr, *Es = nullptr, *Aps = nullptr, *Aes = nullptr, *Bps = nullptr, *Bes = nullptr;
     cudaEvent_t filled = nullptr;
-    std::shared_ptr<std::atomic<int>> inflight = std::make_shared<std::atomic<int>>(0);   // copy-out jobs not yet done
-};
-
-// ------------------------------------------------------------------------------------------------
-// Copy-out pool.  The caller's output arrays are pageable (R vectors, NumPy arrays); a device-to-host copy
-// straight into them stages through the driver and blocks the enqueuing thread, which starves the GPU of
-// sweeps.  Instead the samples leave in pieces of at most kStageBytes: a worker thread waits for the ring
-// set to be filled, copies a piece into its own pinned buffer at PCIe speed and then moves it into the
-// caller's array, several pieces in flight.  One pool per device, started on first use, never torn down.
-// ------------------------------------------------------------------------------------------------
-class CopyPool {
-public:
-    static constexpr size_t kStageBytes = size_t(32) << 20;
-    static constexpr int kWorkers = 4;
-    struct Job { const char *src; char *dst; size_t bytes; cudaEvent_t ready; std::shared_ptr<std::atomic<int>> pending; };
-
-    static CopyPool &of(int device)
-    {
-        static std::mutex mu;
-        static CopyPool *pools[64] = {nullptr};
-        std::lock_guard<std::mutex> lk(mu);
-        if (!pools[device]) pools[device] = new CopyPool(device);
-        return *pools[device];
-    }
-    // copy [src, src+bytes) (device) to dst (pageable host) once `ready` has happened
-    void post(const void *src, void *dst, size_t bytes, cudaEvent_t ready, const std::shared_ptr<std::atomic<int>> &pending)
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        for (size_t off = 0; off < bytes; off += kStageBytes) {
-            pending->fetch_add(1);
-            q_.push_back(Job{static_cast<const char *>(src) + off, static_cast<char *>(dst) + off, std::min(kStageBytes, bytes - off), ready, pending});
-        }
-        cv_.notify_all();
-    }
-    // block until every job counted by `pending` is done; false if a worker met a CUDA error
-    bool wait(const std::shared_ptr<std::atomic<int>> &pending)
-    {
-        std::unique_lock<std::mutex> lk(mu_);
-        done_.wait(lk, [&] { return pending->load() == 0; });
-        return !failed_;
-    }
-    const char *error() const { return err_; }
-
-private:
-    explicit CopyPool(int device) : device_(device)
-    {
-        for (int w = 0; w < kWorkers; ++w) std::thread([this] { run(); }).detach();
-    }
-    void run()
-    {
-        void *stage = nullptr;
-        cudaStream_t st = nullptr;
-        bool ok = cudaSetDevice(device_) == cudaSuccess && cudaHostAlloc(&stage, kStageBytes, cudaHostAllocDefault) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
-        for (;;) {
-            Job j;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return !q_.empty(); });
-                j = q_.front(); q_.pop_front();
-            }
-            cudaError_t e = ok ? cudaEventSynchronize(j.ready) : cudaErrorUnknown;
-            if (e == cudaSuccess) e = cudaMemcpyAsync(stage, j.src, j.bytes, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e == cudaSuccess) std::memcpy(j.dst, stage, j.bytes);
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (e != cudaSuccess) { failed_ = true; err_ = cudaGetErrorString(e); }
-                j.pending->fetch_sub(1);
-            }
-            done_.notify_all();
-        }
-    }
-    int device_;
-    std::mutex mu_;
-    std::condition_variable cv_, done_;
-    std::deque<Job> q_;
-    bool failed_ = false;
-    const char *err_ = "";
+    GroupPtr inflight = sgh::make_group();   // copy-out jobs not yet done
 };
 
 } // namespace
@@ -307,18 +108,23 @@ private:
 struct signer_chain {
     std::shared_ptr<DeviceData> data;
     int device = 0, I = 0, J = 0, Jp = 0, K = 0;
-    size_t nP = 0, nE = 0;
+    size_t nP = 0, nE = 0, nPp = 0, nEp = 0;   // matrix sizes, and padded to 32 doubles inside the state block
+    // one allocation [P | Ap | Bp | E | Ae | Be]: the state goes up and comes back with ONE copy through a pinned buffer
+    double *state_block = nullptr;
+    PinnedBuf hstate;
     double *P = nullptr, *E = nullptr, *Ap = nullptr, *Bp = nullptr, *Ae = nullptr, *Be = nullptr;
     int *Zin[2] = {nullptr, nullptr}, *Znj[2] = {nullptr, nullptr};
     int zcur = 0;
     double *corrE_part = nullptr;
     int n_seg = 0;
     int shard = 0, n_shards = 1, col0 = 0;   // column sharding (signer_gibbs_run_sharded)
-    double *corrE_all = nullptr;             // [n_shards][I*K]: every shard's ordered W E' sum, after the all-reduce
+    double *corrE_all = nullptr;             // [n_shards][I*K]: every shard's ordered W E' sum, after the exchange
     double *col = nullptr, *ll_ring = nullptr;
     int ll_cap = 0;
     double *Zcube = nullptr;
-    double *stats = nullptr;
+    double *stats = nullptr;                 // [8] sufficient statistics of the last keep_par run's samples (EM M-step)
+    bool stats_valid = false;
+    double stats_np = 0, stats_ne = 0;
     double *sumPs = nullptr, *sumEs = nullptr;   // full-length sample stores for the device-side summaries
     unsigned long long *draw_count = nullptr;    // [2] device counters of step-1 draws (allocated on request)
     double *acache_p = nullptr, *acache_e = nullptr;   // [3][I*K], [3][K*J]: A-only terms of the MH ratios (kernels.cuh, ACache)
@@ -334,10 +140,11 @@ struct signer_chain {
     int64_t launches = 0;
     int Pfixed = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    bool borrowed_stream = false;            // `stream` belongs to a peer shard (same-device emulation): never synchronised here
     // the log-likelihood of an evaluation sweep only reads P and E: it runs on its own stream next to the following
     // sweep's z_alloc_fused (which reads them too); the next kernel that writes P or E waits for it
     cudaStream_t ll_stream = nullptr;
-    cudaEvent_t ll_ready = nullptr, ll_done = nullptr;
+    cudaEvent_t ll_ready = nullptr, ll_done = nullptr, cube_done = nullptr;
     bool ll_pending = false;
     Ring ring[2];
     int ring_cap = 0, ring_keep = 0;
@@ -349,22 +156,26 @@ struct signer_chain {
     {
         cudaSetDevice(device);
         if (own_stream) cudaStreamSynchronize(own_stream);
+        if (stream && stream != own_stream && !borrowed_stream) cudaStreamSynchronize(stream);   // a caller's stream (set_stream) must outlive the chain
         if (ll_stream) cudaStreamSynchronize(ll_stream);
-        for (double *p : {P, E, Ap, Bp, Ae, Be, corrE_part, corrE_all, col, ll_ring, Zcube, stats, sumPs, sumEs, acache_p, acache_e}) cudaFree(p);
+        cudaStream_t fs = own_stream;
+        for (void *p : {(void *)state_block, (void *)corrE_part, (void *)corrE_all, (void *)col, (void *)ll_ring, (void *)Zcube, (void *)stats,
+                        (void *)sumPs, (void *)sumEs, (void *)acache_p, (void *)acache_e, (void *)tile_counter, (void *)draw_count, (void *)ll_ticket})
+            dfree(p, fs);
         for (int b = 0; b < 2; ++b) {
-            cudaFree(Zin[b]); cudaFree(Znj[b]);
-            free_ring(ring[b]);
+            dfree(Zin[b], fs); dfree(Znj[b], fs);
+            free_ring(ring[b], fs);
         }
-        cudaFree(tile_counter); cudaFree(draw_count); cudaFree(ll_ticket);
         for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-        if (own_stream) cudaStreamDestroy(own_stream);
+        if (own_stream) { cudaStreamSynchronize(own_stream); cudaStreamDestroy(own_stream); }
         if (ll_stream) cudaStreamDestroy(ll_stream);
         if (ll_ready) cudaEventDestroy(ll_ready);
         if (ll_done) cudaEventDestroy(ll_done);
+        if (cube_done) cudaEventDestroy(cube_done);
     }
-    static void free_ring(Ring &r)
+    static void free_ring(Ring &r, cudaStream_t fs)
     {
-        for (double *p : {r.Ps, r.Es, r.Aps, r.Aes, r.Bps, r.Bes}) cudaFree(p);
+        for (double *p : {r.Ps, r.Es, r.Aps, r.Aes, r.Bps, r.Bes}) dfree(p, fs);
         if (r.filled) cudaEventDestroy(r.filled);
         r = Ring{};
     }
@@ -505,26 +316,6 @@ int launch_loglik(signer_chain *c, double *out)
     return SIGNER_OK;
 }
 
-// Touch every page of a caller-allocated output buffer (it is ours to overwrite) so that the later
-// device-to-host copies land on resident pages; runs on helper threads while the GPU does the burn-in.
-void prefault(double *p, size_t n_doubles)
-{
-    if (!p) return;
-    volatile char *b = reinterpret_cast<volatile char *>(p);
-    const size_t bytes = n_doubles * sizeof(double);
-    if (g_no_hugepage) {
-        // A caller that asked for transparent huge pages (NumPy does for large arrays) makes every first touch wait
-        // for a free 2 MB block -- direct compaction inside the fault, measured as sporadic stalls of up to a second
-        // per call.  These pages are written once and read once: plain 4 KB faults, spread over the helper threads,
-        // are faster and predictable.  (A hint only; R's vectors are not huge-page backed in the first place.)
-        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(p) + 4095) & ~uintptr_t(4095);
-        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(p) + bytes) & ~uintptr_t(4095);
-        if (a1 > a0) madvise(reinterpret_cast<void *>(a0), a1 - a0, MADV_NOHUGEPAGE);
-    }
-    for (size_t off = 0; off < bytes; off += 4096) b[off] = 0;
-    if (bytes) b[bytes - 1] = 0;
-}
-
 int rebuild_a_cache(signer_chain *c)
 {
     a_cache_init<<<(unsigned)((c->nP + 127) / 128), 128, 0, c->stream>>>(c->Ap, c->nP, c->h.var_ap, ACache{c->acache_p, c->acache_p + c->nP, c->acache_p + 2 * c->nP});
@@ -613,15 +404,15 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
     int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes / per_sweep));
     if (c->ring_cap >= cap && c->ring_keep >= keep_par) return SIGNER_OK;
     for (int b = 0; b < 2; ++b) {
-        signer_chain::free_ring(c->ring[b]);
+        signer_chain::free_ring(c->ring[b], c->stream);
         Ring &r = c->ring[b];
-        CU(cudaMalloc(&r.Ps, sizeof(double) * c->nP * cap));
-        CU(cudaMalloc(&r.Es, sizeof(double) * c->nE * cap));
-        CU(cudaMalloc(&r.Bps, sizeof(double) * c->nP * cap));
-        CU(cudaMalloc(&r.Bes, sizeof(double) * c->nE * cap));
+        ST(dalloc(&r.Ps, c->nP * cap, c->stream));
+        ST(dalloc(&r.Es, c->nE * cap, c->stream));
+        ST(dalloc(&r.Bps, c->nP * cap, c->stream));
+        ST(dalloc(&r.Bes, c->nE * cap, c->stream));
         if (keep_par) {
-            CU(cudaMalloc(&r.Aps, sizeof(double) * c->nP * cap));
-            CU(cudaMalloc(&r.Aes, sizeof(double) * c->nE * cap));
+            ST(dalloc(&r.Aps, c->nP * cap, c->stream));
+            ST(dalloc(&r.Aes, c->nE * cap, c->stream));
         }
         CU(cudaEventCreateWithFlags(&r.filled, cudaEventDisableTiming));
     }
@@ -630,14 +421,14 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
 }
 
 // copy chunk `chunk` (sweeps r0 .. r0+cnt-1 of the eval phase) from its ring set to the host: posted to the
-// device's copy-out pool, which waits for the ring set's `filled` event
+// device's transfer pool, which waits for the ring set's `filled` event
 int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signer_outputs *out)
 {
     Ring &r = c->ring[chunk & 1];
-    CopyPool &pool = CopyPool::of(c->device);
+    TransferPool &pool = TransferPool::of(c->device);
     auto cp = [&](double *dst, const double *src, size_t per) {
         if (!dst || !src) return;
-        pool.post(src, dst + per * (size_t)r0, sizeof(double) * per * (size_t)cnt, r.filled, r.inflight);
+        pool.post_d2h(src, dst + per * (size_t)r0, sizeof(double) * per * (size_t)cnt, r.filled, r.inflight);
     };
     if (!c->sumPs) { cp(out->Ps, r.Ps, c->nP); cp(out->Es, r.Es, c->nE); }   // else: from the full-length stores at the end
     cp(out->Bps, r.Bps, c->nP); cp(out->Bes, r.Bes, c->nE);
@@ -645,52 +436,93 @@ int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signe
     return SIGNER_OK;
 }
 
-// the ring set's samples have all reached the caller's arrays (it may be refilled)
-int wait_ring(signer_chain *c, Ring &r)
+// every job of the group has finished; a failure is reported once and the group starts afresh
+int wait_group(int device, GroupPtr &g, const char *what)
 {
-    if (!CopyPool::of(c->device).wait(r.inflight)) return fail(SIGNER_ERR_CUDA, CopyPool::of(c->device).error());
-    return SIGNER_OK;
+    if (TransferPool::of(device).wait(g)) return SIGNER_OK;
+    const std::string err = g->err;
+    g = sgh::make_group();
+    return fail(SIGNER_ERR_CUDA, std::string(what) + ": " + err);
 }
+
+// the ring set's samples have all reached the caller's arrays (it may be refilled)
+int wait_ring(signer_chain *c, Ring &r) { return wait_group(c->device, r.inflight, "sample copy-out"); }
 
 // Phat / Ehat from the full-length sample stores (see include/signer_gibbs.h)
 int device_summaries(signer_chain *c, int R, double *Phat, double *Ehat)
 {
-    double *s = nullptr, *T = nullptr, *med = nullptr;
+    DevTemp s, T, med;
     const size_t nmax = std::max(c->nP, c->nE);
-    CU(cudaMalloc(&s, sizeof(double) * (size_t)R * c->K));
-    CU(cudaMalloc(&T, sizeof(double) * nmax * (size_t)R));
-    CU(cudaMalloc(&med, sizeof(double) * nmax));
-    sig_sums<<<(R * c->K + 127) / 128, 128, 0, c->stream>>>(c->sumPs, c->I, c->K, R, s);
+    ST(s.get(sizeof(double) * (size_t)R * c->K, c->stream));
+    ST(T.get(sizeof(double) * nmax * (size_t)R, c->stream));
+    ST(med.get(sizeof(double) * nmax, c->stream));
+    sig_sums<<<(R * c->K + 127) / 128, 128, 0, c->stream>>>(c->sumPs, c->I, c->K, R, s.as<double>());
     for (int mode = 0; mode < 2; ++mode) {
         const size_t n = mode == 0 ? c->nP : c->nE;
         double *dst = mode == 0 ? Phat : Ehat;
         if (!dst) continue;
         norm_transpose<<<dim3((unsigned)((n + 31) / 32), (unsigned)((R + 31) / 32)), dim3(32, 8), 0, c->stream>>>(
-            mode == 0 ? c->sumPs : c->sumEs, s, (int)n, R, c->I, c->K, mode, T);
-        median_rows<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>(T, (int)n, R, med);
+            mode == 0 ? c->sumPs : c->sumEs, s.as<double>(), (int)n, R, c->I, c->K, mode, T.as<double>());
+        median_rows<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>(T.as<double>(), (int)n, R, med.as<double>());
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(dst, med, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(dst, med.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         c->launches += 2;
     }
     c->launches += 1;
-    cudaFree(s); cudaFree(T); cudaFree(med);
     return SIGNER_OK;
 }
 
+// the six state matrices come back with one copy of the state block through the chain's pinned buffer
 int fetch_state(signer_chain *c, signer_outputs *out)
 {
     CU(cudaSetDevice(c->device));
+    const bool any_state = out->P || out->Ap || out->Bp || out->E || out->Ae || out->Be;
+    const size_t sd = 3 * (c->nPp + c->nEp);
+    const size_t need = sd * sizeof(double) + (c->nP + c->nE) * sizeof(int);
+    if (!c->hstate.get(need)) return fail(SIGNER_ERR_NOMEM, "pinned staging buffer");
+    double *hs = c->hstate.as<double>();
+    int *hz = reinterpret_cast<int *>(hs + sd);
+    if (any_state) CU(cudaMemcpyAsync(hs, c->state_block, sd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out->Zin) CU(cudaMemcpyAsync(hz, c->Zin[c->zcur], c->nP * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (out->Znj) CU(cudaMemcpyAsync(hz + c->nP, c->Znj[c->zcur], c->nE * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    auto cp = [&](void *dst, const void *src, size_t bytes) -> int {
-        if (!dst) return SIGNER_OK;
-        CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
-        return SIGNER_OK;
-    };
-    ST(cp(out->P, c->P, c->nP * 8)); ST(cp(out->Ap, c->Ap, c->nP * 8)); ST(cp(out->Bp, c->Bp, c->nP * 8));
-    ST(cp(out->E, c->E, c->nE * 8)); ST(cp(out->Ae, c->Ae, c->nE * 8)); ST(cp(out->Be, c->Be, c->nE * 8));
-    ST(cp(out->Zin, c->Zin[c->zcur], c->nP * 4)); ST(cp(out->Znj, c->Znj[c->zcur], c->nE * 4));
+    auto cp = [&](double *dst, size_t off, size_t n) { if (dst) std::memcpy(dst, hs + off, n * sizeof(double)); };
+    cp(out->P, 0, c->nP); cp(out->Ap, c->nPp, c->nP); cp(out->Bp, 2 * c->nPp, c->nP);
+    cp(out->E, 3 * c->nPp, c->nE); cp(out->Ae, 3 * c->nPp + c->nEp, c->nE); cp(out->Be, 3 * c->nPp + 2 * c->nEp, c->nE);
+    if (out->Zin) std::memcpy(out->Zin, hz, c->nP * sizeof(int));
+    if (out->Znj) std::memcpy(out->Znj, hz + c->nP, c->nE * sizeof(int));
     return SIGNER_OK;
+}
+
+// Reduce the given I x J x K cube (pageable host memory; columns [c0, c0+Jl) of every slice) to the chain's
+// statistics Zin[0], Znj[0] (zeroed on c->stream before): pieces of at most 4 MB go through the transfer pool, each
+// worker hands its piece to zslab_reduce on its own stream.
+int reduce_cube(signer_chain *c, const double *Z, int Jfull, int c0)
+{
+    cudaEvent_t ready = nullptr;
+    CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    struct EventGuard { cudaEvent_t e; ~EventGuard() { cudaEventDestroy(e); } } eg{ready};
+    CU(cudaEventRecord(ready, c->stream));
+    TransferPool &pool = TransferPool::of(c->device);
+    GroupPtr g = sgh::make_group();
+    const int I = c->I, Jl = c->J, K = c->K;
+    const int nj_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)Jl, (size_t(4) << 20) / ((size_t)I * sizeof(double))));
+    int *Zin = c->Zin[0], *Znj = c->Znj[0];
+    const int use_smem = ((size_t)I * sizeof(int) <= 32 * 1024) ? 1 : 0;
+    for (int k = 0; k < K; ++k)
+        for (int ja = 0; ja < Jl; ja += nj_max) {
+            const int nj = std::min(nj_max, Jl - ja);
+            const double *src = Z + (size_t)I * Jfull * k + (size_t)I * (c0 + ja);
+            pool.post_h2d_hook(src, (size_t)I * nj * sizeof(double), ready, g,
+                               [=](const void *dev, size_t, cudaStream_t st) -> cudaError_t {
+                                   zslab_reduce<<<(nj + 63) / 64, 256, use_smem ? (size_t)I * sizeof(int) : 0, st>>>(
+                                       static_cast<const double *>(dev), I, nj, ja, K, k, use_smem, Zin, Znj);
+                                   return cudaGetLastError();
+                               });
+        }
+    c->launches += (int64_t)K * ((Jl + nj_max - 1) / nj_max);
+    return wait_group(c->device, g, "upload of the Z cube");
 }
 
 int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st, const signer_opts *o, signer_chain **out,
@@ -703,9 +535,11 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     if ((long long)K * data->J >= (1LL << 31) || (long long)data->I * K >= (1LL << 31)) return fail(SIGNER_ERR_ARG, "K*J and I*K must be below 2^31");
     if (!st->P || !st->E || !st->Ap || !st->Bp || !st->Ae || !st->Be) return fail(SIGNER_ERR_ARG, "state: P,E,Ap,Bp,Ae,Be must be non-null");
     CU(cudaSetDevice(data->device));
+    ST(ensure_device_setup(data->device));
     std::unique_ptr<signer_chain> c(new signer_chain());
     c->data = data; c->device = data->device; c->I = data->I; c->J = data->J; c->Jp = data->Jp; c->K = K;
     c->nP = (size_t)c->I * K; c->nE = (size_t)K * c->J;
+    c->nPp = (c->nP + 31) / 32 * 32; c->nEp = (c->nE + 31) / 32 * 32;
     c->h = Hyper{o->ap, o->bp, o->ae, o->be, o->lp, o->le, o->var_ap, o->var_ae};
     c->key = Key{(uint32_t)o->seed, (uint32_t)(o->seed >> 32)};
     c->sweep0 = o->sweep0; c->Pfixed = o->Pfixed ? 1 : 0;
@@ -713,31 +547,39 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     CU(cudaStreamCreateWithFlags(&c->ll_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ll_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ll_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->cube_done, cudaEventDisableTiming));
     c->stream = c->own_stream;
-    auto up = [&](double **dst, const double *src, size_t n) -> int {
-        CU(cudaMalloc(dst, n * sizeof(double)));
-        CU(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        return SIGNER_OK;
-    };
-    ST(up(&c->P, st->P, c->nP)); ST(up(&c->Ap, st->Ap, c->nP)); ST(up(&c->Bp, st->Bp, c->nP));
-    ST(up(&c->E, st->E, c->nE)); ST(up(&c->Ae, st->Ae, c->nE)); ST(up(&c->Be, st->Be, c->nE));
+    cudaStream_t s = c->stream;
+    // the state: gathered into the pinned buffer, one copy up
+    {
+        const size_t sd = 3 * (c->nPp + c->nEp);
+        if (!c->hstate.get(sd * sizeof(double) + (c->nP + c->nE) * sizeof(int))) return fail(SIGNER_ERR_NOMEM, "pinned staging buffer");
+        double *hs = c->hstate.as<double>();
+        std::memcpy(hs, st->P, c->nP * 8); std::memcpy(hs + c->nPp, st->Ap, c->nP * 8); std::memcpy(hs + 2 * c->nPp, st->Bp, c->nP * 8);
+        std::memcpy(hs + 3 * c->nPp, st->E, c->nE * 8); std::memcpy(hs + 3 * c->nPp + c->nEp, st->Ae, c->nE * 8);
+        std::memcpy(hs + 3 * c->nPp + 2 * c->nEp, st->Be, c->nE * 8);
+        ST(dalloc(&c->state_block, sd, s));
+        CU(cudaMemcpyAsync(c->state_block, hs, sd * sizeof(double), cudaMemcpyHostToDevice, s));
+        c->P = c->state_block; c->Ap = c->P + c->nPp; c->Bp = c->Ap + c->nPp;
+        c->E = c->Bp + c->nPp; c->Ae = c->E + c->nEp; c->Be = c->Ae + c->nEp;
+    }
     for (int b = 0; b < 2; ++b) {
-        CU(cudaMalloc(&c->Zin[b], c->nP * sizeof(int)));
-        CU(cudaMalloc(&c->Znj[b], c->nE * sizeof(int)));
-        CU(cudaMemsetAsync(c->Zin[b], 0, c->nP * sizeof(int), c->stream));
-        CU(cudaMemsetAsync(c->Znj[b], 0, c->nE * sizeof(int), c->stream));
+        ST(dalloc(&c->Zin[b], c->nP, s));
+        ST(dalloc(&c->Znj[b], c->nE, s));
+        CU(cudaMemsetAsync(c->Zin[b], 0, c->nP * sizeof(int), s));
+        CU(cudaMemsetAsync(c->Znj[b], 0, c->nE * sizeof(int), s));
     }
     c->n_seg = (c->J + kSeg - 1) / kSeg;
-    CU(cudaMalloc(&c->corrE_part, sizeof(double) * (size_t)c->n_seg * c->nP));
-    CU(cudaMalloc(&c->col, sizeof(double) * (size_t)data->n2));
-    CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)data->n2, c->stream));
-    CU(cudaMalloc(&c->tile_counter, sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned long long), c->stream));
-    CU(cudaMalloc(&c->ll_ticket, sizeof(unsigned)));
-    CU(cudaMemsetAsync(c->ll_ticket, 0, sizeof(unsigned), c->stream));
-    CU(cudaMalloc(&c->stats, 8 * sizeof(double)));
-    CU(cudaMalloc(&c->acache_p, 3 * c->nP * sizeof(double)));
-    CU(cudaMalloc(&c->acache_e, 3 * c->nE * sizeof(double)));
+    ST(dalloc(&c->corrE_part, (size_t)c->n_seg * c->nP, s));
+    ST(dalloc(&c->col, (size_t)data->n2, s));
+    CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)data->n2, s));
+    ST(dalloc(&c->tile_counter, 1, s));
+    CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned long long), s));
+    ST(dalloc(&c->ll_ticket, 1, s));
+    CU(cudaMemsetAsync(c->ll_ticket, 0, sizeof(unsigned), s));
+    ST(dalloc(&c->stats, 8, s));
+    ST(dalloc(&c->acache_p, 3 * c->nP, s));
+    ST(dalloc(&c->acache_e, 3 * c->nE, s));
     ST(rebuild_a_cache(c.get()));
 
     // launch geometry
@@ -745,7 +587,6 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->n_chunks = (c->n_batches + kZChunk - 1) / kZChunk;
     c->z_warp_smem = (int)z_smem_bytes_per_warp(K);
     c->z_zin_smem = (c->nP * sizeof(int) <= (size_t)kZinSmemMax) ? 1 : 0;
-    ST(ensure_device_setup(c->device));
     // block size: the configuration that keeps the most warps resident per SM (at most kZMaxWarps: the register
     // file holds that many at the kernel's 80 registers); ties go to fewer, larger blocks (fewer Zin accumulators
     // in shared memory, which leaves more of the SM's 256 KB to L1)
@@ -768,35 +609,20 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->z_grid = std::max(1, std::min((c->n_chunks + best_w - 1) / best_w, best_b * sms));
     c->ksplit = (K + kEGroup - 1) / kEGroup;
 
-
     // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device
     if (deferred_init) {                                  // a column shard: its peers take part (sharded_run)
-        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(s));
         *out = c.release();
         return SIGNER_OK;
     }
-    if (st->Z) {
-        double *slab[2] = {nullptr, nullptr};
-        const size_t ns = (size_t)c->I * c->J;
-        CU(cudaMalloc(&slab[0], ns * sizeof(double)));
-        CU(cudaMalloc(&slab[1], ns * sizeof(double)));
-        for (int k = 0; k < K; ++k) {
-            CU(cudaMemcpyAsync(slab[k & 1], st->Z + ns * k, ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            zslab_reduce<<<(c->J + 127) / 128, 128, 0, c->stream>>>(slab[k & 1], c->I, c->J, K, k, c->Zin[0], c->Znj[0]);
-        }
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaFree(slab[0])); CU(cudaFree(slab[1]));
-        c->zcur = 0;
-    } else {
-        c->zcur = 0;
-        ST(launch_z(c.get(), c->sweep0, kStZinit, nullptr));
-    }
+    c->zcur = 0;
+    if (st->Z) ST(reduce_cube(c.get(), st->Z, c->J, 0));
+    else ST(launch_z(c.get(), c->sweep0, kStZinit, nullptr));
     if (!c->Pfixed) {   // W E' of the initial E, in case step 2 comes before step 3
         Ops none{0, 0u};
         ST(launch_e(c.get(), c->sweep0, none, 1, nullptr, nullptr, nullptr));
     }
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(s));                         // the pinned state buffer may be reused from here on
     *out = c.release();
     return SIGNER_OK;
 }
@@ -806,26 +632,35 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     if (burn < 0 || eval < 0) return fail(SIGNER_ERR_ARG, "burn and eval must be non-negative");
     CU(cudaSetDevice(c->device));
     keep_par = keep_par ? 1 : 0;
+    // Sample rings: needed when samples leave for the host, and for a run that keeps everything on the device (out == NULL:
+    // the EM loop reads their statistics).  A caller that asks only for log-likelihoods / BICs (the model-selection path,
+    // signer_gibbs_batch) gets no ring stores at all.
+    const bool want_rings = eval > 0 && (!out || out->Ps || out->Es || out->Bps || out->Bes || (keep_par && (out->Aps || out->Aes)));
     if (eval > 0) {
-        ST(ensure_rings(c, eval, keep_par));
+        if (want_rings) ST(ensure_rings(c, eval, keep_par));
         if (c->ll_cap < eval) {
-            cudaFree(c->ll_ring); c->ll_ring = nullptr; c->ll_cap = 0;
-            CU(cudaMalloc(&c->ll_ring, sizeof(double) * (size_t)eval));
+            dfree(c->ll_ring, c->stream); c->ll_ring = nullptr; c->ll_cap = 0;
+            ST(dalloc(&c->ll_ring, (size_t)eval, c->stream));
             c->ll_cap = eval;
         }
     }
     double *zcube = nullptr;
     if (keep_par && out && out->Zs && eval > 0) {
-        if (!c->Zcube) CU(cudaMalloc(&c->Zcube, sizeof(double) * (size_t)c->I * c->J * c->K));
+        if (!c->Zcube) ST(dalloc(&c->Zcube, (size_t)c->I * c->J * c->K, c->stream));
         zcube = c->Zcube;
     }
     const bool summ = out && eval > 0 && (out->Phat || out->Ehat);
     if (summ) {                                           // full-length stores for Ps and Es
-        cudaFree(c->sumPs); cudaFree(c->sumEs); c->sumPs = c->sumEs = nullptr;
-        CU(cudaMalloc(&c->sumPs, sizeof(double) * c->nP * (size_t)eval));
-        CU(cudaMalloc(&c->sumEs, sizeof(double) * c->nE * (size_t)eval));
+        dfree(c->sumPs, c->stream); dfree(c->sumEs, c->stream); c->sumPs = c->sumEs = nullptr;
+        ST(dalloc(&c->sumPs, c->nP * (size_t)eval, c->stream));
+        ST(dalloc(&c->sumEs, c->nE * (size_t)eval, c->stream));
     }
-    const int total = burn + eval, cap = std::max(1, c->ring_cap);
+    const bool do_stats = want_rings && keep_par;         // EM M-step statistics of (Aps, Bps), (Aes, Bes), accumulated per chunk
+    if (eval > 0) {
+        c->stats_valid = false;
+        if (do_stats) CU(cudaMemsetAsync(c->stats, 0, 8 * sizeof(double), c->stream));
+    }
+    const int total = burn + eval, cap = std::max(1, want_rings ? c->ring_cap : eval);
     int chunk_r0 = 0;
     std::vector<std::thread> faulters;
     auto join_faulters = [&]() { for (auto &t : faulters) if (t.joinable()) t.join(); faulters.clear(); };
@@ -833,7 +668,8 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         const size_t R = (size_t)eval;
         double *bufs[7] = {out->Es, out->Bes, keep_par ? out->Aes : nullptr, out->Ps, out->Bps, keep_par ? out->Aps : nullptr, zcube ? out->Zs : nullptr};
         const size_t lens[7] = {c->nE * R, c->nE * R, c->nE * R, c->nP * R, c->nP * R, c->nP * R, (size_t)c->I * c->J * c->K};
-        // large arrays are touched by several threads each (page faults scale across threads)
+        // large arrays are touched by several threads each (page faults scale across threads); the touch is an atomic
+        // no-op, so it can never undo a copy-out that has already landed (host_util.cu)
         const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
         const size_t max_threads = std::min<size_t>(32, hw / 2);
         size_t big_bytes = 0;
@@ -842,12 +678,15 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             if (!bufs[b] || lens[b] * sizeof(double) < (size_t(8) << 20)) continue;
             const size_t parts = std::max<size_t>(1, std::min<size_t>(max_threads, max_threads * (lens[b] * sizeof(double)) / big_bytes));
             const size_t step = ((lens[b] + parts - 1) / parts + 511) / 512 * 512;       // whole pages
-            for (size_t off = 0; off < lens[b]; off += step) faulters.emplace_back(prefault, bufs[b] + off, std::min(step, lens[b] - off));
+            for (size_t off = 0; off < lens[b]; off += step)
+                faulters.emplace_back(sgh::prefault, (void *)(bufs[b] + off), std::min(step, lens[b] - off) * sizeof(double));
         }
     }
     struct Joiner { std::function<void()> f; ~Joiner() { f(); } } joiner{join_faulters};
     // whatever way this call ends, no copy-out job may outlive it: they write into the caller's arrays
-    Joiner drain{[c, out]() { if (out) { CopyPool &p = CopyPool::of(c->device); p.wait(c->ring[0].inflight); p.wait(c->ring[1].inflight); } }};
+    Joiner drain{[c, out]() { if (out) { TransferPool &p = TransferPool::of(c->device); p.wait(c->ring[0].inflight); p.wait(c->ring[1].inflight); } }};
+    GroupPtr cube_group = sgh::make_group();
+    Joiner drain_cube{[c, &cube_group]() { TransferPool::of(c->device).wait(cube_group); }};
     for (int k = 0; k < total; ++k) {
         const uint32_t sweep = c->sweep0 + (uint32_t)c->sweeps_done;
         int order[7];
@@ -859,17 +698,25 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         } else {
             const int r = k - burn, chunk = r / cap, slot = r % cap;
             Ring &rg = c->ring[chunk & 1];
-            if (slot == 0 && chunk >= 2 && out) ST(wait_ring(c, rg));          // the set's previous chunk has left the device
             Slots s;
-            s.Ps = rg.Ps + c->nP * slot; s.Es = rg.Es + c->nE * slot;
-            s.Bps = rg.Bps + c->nP * slot; s.Bes = rg.Bes + c->nE * slot;
-            if (keep_par) { s.Aps = rg.Aps + c->nP * slot; s.Aes = rg.Aes + c->nE * slot; }
+            if (want_rings) {
+                if (slot == 0 && chunk >= 2 && out) ST(wait_ring(c, rg));      // the set's previous chunk has left the device
+                s.Ps = rg.Ps + c->nP * slot; s.Es = rg.Es + c->nE * slot;
+                s.Bps = rg.Bps + c->nP * slot; s.Bes = rg.Bes + c->nE * slot;
+                if (keep_par) { s.Aps = rg.Aps + c->nP * slot; s.Aes = rg.Aes + c->nE * slot; }
+            }
             if (summ) { s.Ps = c->sumPs + c->nP * (size_t)r; s.Es = c->sumEs + c->nE * (size_t)r; }
             const bool last = (k == total - 1);
             // Zs keeps only the latest Z (src/gibbs_2.cpp:323): store the cube in the last sweep only
             ST(enqueue_sweep(c, sweep, order, &s, last ? zcube : nullptr));
             ST(launch_loglik(c, c->ll_ring + r));
-            if (slot == cap - 1 || last) {
+            if (want_rings && (slot == cap - 1 || last)) {
+                if (do_stats) {
+                    stats_reduce<<<256, 256, 0, c->stream>>>(rg.Aps, rg.Bps, c->nP * (size_t)(slot + 1), c->stats);
+                    stats_reduce<<<1024, 256, 0, c->stream>>>(rg.Aes, rg.Bes, c->nE * (size_t)(slot + 1), c->stats + 4);
+                    CU(cudaGetLastError());
+                    c->launches += 2;
+                }
                 CU(cudaEventRecord(rg.filled, c->stream));
                 if (out) ST(flush_chunk(c, chunk, chunk_r0, slot + 1, keep_par, out));
                 chunk_r0 += cap;
@@ -879,19 +726,23 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     }
     ST(wait_loglik(c));                                    // the launching stream ends after the last log-likelihood
     c->last_eval = eval;
+    if (eval > 0 && do_stats) { c->stats_valid = true; c->stats_np = (double)c->nP * eval; c->stats_ne = (double)c->nE * eval; }
     if (out && eval > 0) {
-        CU(cudaStreamSynchronize(c->stream));
-        ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1]));
-        join_faulters();
         if (zcube && out->Zs) {
-            // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined
-            CU(cudaMemcpy(out->Zs, zcube, sizeof(double) * (size_t)c->I * c->J * c->K, cudaMemcpyDeviceToHost));
+            // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined.  The cube leaves
+            // through the transfer pool like the samples (pageable destination).
+            CU(cudaEventRecord(c->cube_done, c->stream));
+            TransferPool::of(c->device).post_d2h(zcube, out->Zs, sizeof(double) * (size_t)c->I * c->J * c->K, c->cube_done, cube_group);
         }
+        CU(cudaStreamSynchronize(c->stream));
+        if (want_rings) { ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1])); }
+        ST(wait_group(c->device, cube_group, "copy-out of the Z cube"));
+        join_faulters();
         if (summ) {
             if (out->Ps) CU(cudaMemcpy(out->Ps, c->sumPs, sizeof(double) * c->nP * (size_t)eval, cudaMemcpyDeviceToHost));
             if (out->Es) CU(cudaMemcpy(out->Es, c->sumEs, sizeof(double) * c->nE * (size_t)eval, cudaMemcpyDeviceToHost));
             ST(device_summaries(c, eval, out->Phat, out->Ehat));
-            cudaFree(c->sumPs); cudaFree(c->sumEs); c->sumPs = c->sumEs = nullptr;
+            dfree(c->sumPs, c->stream); dfree(c->sumEs, c->stream); c->sumPs = c->sumEs = nullptr;
         }
         if (out->loglik || out->bic) {
             std::vector<double> ll((size_t)eval);
@@ -953,7 +804,7 @@ struct ShardSet {
     void **ptr_tab = nullptr;        // device table of buffer pointers for the same-device emulation
     ~ShardSet()
     {
-        for (auto *c : sh) delete c;
+        for (auto it = sh.rbegin(); it != sh.rend(); ++it) delete *it;     // shard 0 last: emulated shards launch on its stream
         for (auto cm : comms) if (cm && nccl.CommDestroy) nccl.CommDestroy(cm);
         if (ptr_tab) cudaFree(ptr_tab);
     }
@@ -1081,8 +932,8 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         ST(chain_create(d, K, &sg, &og, &c, /*deferred_init=*/true));
         S.sh.push_back(c);
         c->shard = g; c->n_shards = n_dev; c->col0 = c0;
-        CU(cudaMalloc(&c->corrE_all, sizeof(double) * c->nP * n_dev));
-        if (S.same_device && g > 0) { CU(cudaStreamSynchronize(c->stream)); c->stream = S.sh[0]->stream; }   // one stream: plain ordering
+        ST(dalloc(&c->corrE_all, c->nP * (size_t)n_dev, c->stream));
+        if (S.same_device && g > 0) { CU(cudaStreamSynchronize(c->stream)); c->stream = S.sh[0]->stream; c->borrowed_stream = true; }   // one stream: plain ordering
     }
     if (S.same_device) { CU(cudaSetDevice(devices[0])); CU(cudaMalloc(&S.ptr_tab, sizeof(void *) * n_dev)); }
     ST(shard_sync(S));
@@ -1092,16 +943,7 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         for (int g = 0; g < n_dev; ++g) {
             signer_chain *c = S.sh[g];
             CU(cudaSetDevice(c->device));
-            double *slab = nullptr;
-            const size_t ns = (size_t)I * c->J;
-            CU(cudaMalloc(&slab, ns * sizeof(double)));
-            for (int k = 0; k < K; ++k) {
-                CU(cudaMemcpyAsync(slab, st->Z + (size_t)I * J * k + (size_t)I * c->col0, ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-                zslab_reduce<<<(c->J + 127) / 128, 128, 0, c->stream>>>(slab, I, c->J, K, k, c->Zin[0], c->Znj[0]);
-            }
-            CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(c->stream));
-            CU(cudaFree(slab));
+            ST(reduce_cube(c, st->Z, J, c->col0));
             c->zcur = 0;
         }
         std::vector<int *> zin(n_dev);
@@ -1120,10 +962,10 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         for (auto *c : S.sh) cap = std::min(cap, c->ring_cap);
         signer_chain *c0 = S.sh[0];
         CU(cudaSetDevice(c0->device));
-        CU(cudaMalloc(&c0->ll_ring, sizeof(double) * (size_t)eval)); c0->ll_cap = eval;
+        ST(dalloc(&c0->ll_ring, (size_t)eval, c0->stream)); c0->ll_cap = eval;
     }
     const bool want_cube = keep_par && out->Zs && eval > 0;
-    if (want_cube) for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); CU(cudaMalloc(&c->Zcube, sizeof(double) * (size_t)I * c->J * K)); }
+    if (want_cube) for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); ST(dalloc(&c->Zcube, (size_t)I * c->J * K, c->stream)); }
 
     auto flush = [&](int r0, int cnt) -> int {            // ring slots 0..cnt-1 hold eval sweeps r0..r0+cnt-1
         ST(shard_sync(S));
@@ -1296,18 +1138,14 @@ int signer_chain_fetch_state(signer_chain *c, signer_outputs *out)
 int signer_chain_fetch_stats(signer_chain *c, double stats[8])
 {
     if (!c || !stats) return fail(SIGNER_ERR_ARG, "null argument");
-    if (c->last_eval <= 0 || c->last_eval > c->ring_cap || !c->ring_keep)
-        return fail(SIGNER_ERR_ARG, "fetch_stats needs a preceding run with keep_par and eval within the device ring");
+    // accumulated on the device chunk by chunk while the last keep_par run stored its samples (chain_run), so the
+    // M-step does not depend on the evaluation sweeps fitting into one ring set
+    if (!c->stats_valid)
+        return fail(SIGNER_ERR_ARG, "fetch_stats needs a preceding run with keep_par and eval > 0 that stored its samples");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemsetAsync(c->stats, 0, 8 * sizeof(double), c->stream));
-    const Ring &r = c->ring[0];
-    const size_t np = c->nP * (size_t)c->last_eval, ne = c->nE * (size_t)c->last_eval;
-    stats_reduce<<<256, 256, 0, c->stream>>>(r.Aps, r.Bps, np, c->stats);
-    stats_reduce<<<1024, 256, 0, c->stream>>>(r.Aes, r.Bes, ne, c->stats + 4);
-    CU(cudaGetLastError());
     CU(cudaMemcpyAsync(stats, c->stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    stats[3] = (double)np; stats[7] = (double)ne;
+    stats[3] = c->stats_np; stats[7] = c->stats_ne;
     return SIGNER_OK;
 }
 
@@ -1341,10 +1179,10 @@ int signer_chain_draw_counts(signer_chain *c, int32_t enable, uint64_t counts[2]
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     if (counts) { counts[0] = counts[1] = 0; }
-    if (c->draw_count && counts) CU(cudaMemcpy(counts, c->draw_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (enable && !c->draw_count) CU(cudaMalloc(&c->draw_count, 2 * sizeof(unsigned long long)));
-    if (c->draw_count) CU(cudaMemset(c->draw_count, 0, 2 * sizeof(unsigned long long)));
-    if (!enable && c->draw_count) { cudaFree(c->draw_count); c->draw_count = nullptr; }
+    if (c->draw_count && counts) { CU(cudaMemcpyAsync(counts, c->draw_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); }
+    if (enable && !c->draw_count) ST(dalloc(&c->draw_count, 2, c->stream));
+    if (c->draw_count) { CU(cudaMemsetAsync(c->draw_count, 0, 2 * sizeof(unsigned long long), c->stream)); CU(cudaStreamSynchronize(c->stream)); }
+    if (!enable && c->draw_count) { dfree(c->draw_count, c->stream); c->draw_count = nullptr; }
     return SIGNER_OK;
 }
 
@@ -1374,18 +1212,41 @@ int signer_draw_ceiling(int32_t device, double *draws_per_s)
 
 void signer_chain_destroy(signer_chain *c) { delete c; }
 
+void signer_release_caches(void)
+{
+    sgh::cohort_cache_clear();
+    sgh::PinnedCache::clear();
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int d = 0; d < n; ++d) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+}
+
 int signer_gibbs_run(const signer_problem *pr, const signer_state *st, const signer_opts *o, signer_outputs *out)
 {
     g_err.clear();
     if (!pr || !st || !o || !out) return fail(SIGNER_ERR_ARG, "null argument");
+    static const bool trace = [] { const char *e = std::getenv("SIGNER_TRACE"); return e && e[0] == '1'; }();   // phase times on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+    std::shared_ptr<DeviceData> d;
+    ST(upload_data(o->device, pr->I, pr->J, pr->M, pr->W, d));
+    const double t_data = ms_since(t0);
     signer_chain *c = nullptr;
-    ST(signer_chain_create(pr, st, o, &c));
+    ST(chain_create(d, pr->K, st, o, &c));
+    const double t_create = ms_since(t0);
     const auto t_loop = std::chrono::steady_clock::now();
     const int rc = chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, out);
-    g_loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
+    g_loop_ms = ms_since(t_loop);
     const std::string keep = g_err;
     signer_chain_destroy(c);
     g_err = keep;
+    if (trace)
+        std::fprintf(stderr, "[signer_gibbs_run] cohort %.2f ms, chain create %.2f ms, sweeps + copy-out %.2f ms, destroy %.2f ms\n", t_data,
+                     t_create - t_data, g_loop_ms, ms_since(t0) - t_create - g_loop_ms);
     return rc;
 }
 
@@ -1459,6 +1320,8 @@ int signer_gibbs_run_sharded(const signer_problem *pr, const signer_state *st, c
     if (!pr || !st || !o || !out || !devices) return fail(SIGNER_ERR_ARG, "null argument");
     if (o->Zfixed || o->Thetafixed || o->Afixed)
         return fail(SIGNER_ERR_UNSUPPORTED, "Zfixed/Thetafixed/Afixed=TRUE are not reachable from signeR and not implemented");
+    if (out->Phat || out->Ehat)
+        return fail(SIGNER_ERR_UNSUPPORTED, "Phat/Ehat (device-side posterior medians) are not available on the column-sharded path");
     return sharded_run(pr, st, o, out, devices, n_devices);
 }
 

@@ -2,11 +2,10 @@
 R/signeR.R:62-230 and R/Optimal_sigs.R:1-168 on top of the CUDA sampler.
 
 The reference evaluates candidates as `future`s on availableCores()-1 PSOCK worker processes and
-polls them, so WHICH candidates end up evaluated depends on timing.  Here a whole wave of
-candidates is evaluated by one batch call (one host thread per GPU, signer_gibbs_batch) and the
-reference's comparison rule (median BIC, keep-best set, downhill stop, step halving, ties to the
-smaller n) is then replayed on the results in launch order, which is what the reference does when
-its futures resolve in order.
+polls them.  Optimal_sigs below is a statement-by-statement transcription of R/Optimal_sigs.R; the
+only substitution is the future itself: a launched candidate is queued, and the first poll of a
+queued candidate evaluates everything queued in one batch call (one host thread per GPU,
+signer_gibbs_batch) -- the reference's behaviour when its workers finish between two polls.
 """
 import ctypes as C
 import math
@@ -20,8 +19,8 @@ HH_DEFAULT = dict(ap=0.8005, bp=0.043, ae=2.0506, be=1.325, lp=5.3329, le=1.436)
 
 
 def _compare(thisbics, nmax, values, significance, pcrit):
-    """One 'compare k and nmax' block of R/Optimal_sigs.R:38-69.  Returns the new nmax list for
-    candidate k (appended by the caller when it survives)."""
+    """The 'compare k and nmax' block of R/Optimal_sigs.R:38-62 (and :112-137): one verdict per member of nmax,
+    1 = k is better, -1 = k is worse, 0 = tie (or not significantly different)."""
     thismedian = np.median(thisbics)
     testeq = []
     for n in nmax:
@@ -36,48 +35,113 @@ def _compare(thisbics, nmax, values, significance, pcrit):
     return testeq
 
 
-def Optimal_sigs(testfun, liminf, limsup, step, significance=False, pcrit=0.05, batchfun=None):
-    """testfun(n) -> [bics, HH]; batchfun(list_of_n) -> {n: [bics, HH]} evaluates a wave at once
-    (defaults to calling testfun one by one).  Returns [nopt, evaluated n (ascending), results]."""
+def _update_nmax(k, thisbics, nmax, values, significance, pcrit):
+    """R/Optimal_sigs.R:63-65 (and :138-139): keep those n not worse than k; keep k if no other n is better."""
+    testeq = _compare(thisbics, nmax, values, significance, pcrit)
+    nmax = [n for n, t in zip(nmax, testeq) if t in (0, -1)]
+    if len(nmax) == 0 or min(testeq) >= 0:
+        nmax.append(k)
+    return nmax
+
+
+def Optimal_sigs(testfun, liminf, limsup, step, significance=False, pcrit=0.05, parplan="multisession", *,
+                 batchfun=None, ncores=None):
+    """Literal transcription of R/Optimal_sigs.R:1-168, statement by statement (line cites on the right).
+
+    testfun(n) -> [bics, HH].  The reference launches testfun(n) as `future`s on worker processes and polls
+    `resolved()`; here `launch` queues a candidate and the first poll of a queued candidate evaluates EVERYTHING
+    queued so far in one call of batchfun(list_of_n) -> {n: [bics, HH]} (one multi-GPU batch, signer_gibbs_batch).
+    That is the reference's behaviour when its workers finish between two polls; like there, which candidates get
+    evaluated and compared depends on `ncores` (parallel::detectCores()-1, :17): candidates still running when the
+    coarse search turns downhill are finished but never compared (:29, :92-98), candidates not yet launched at that
+    point are dropped (eval_latter is overwritten, :99-105), and the refinement takes ONE element of to_eval when
+    more are left than workers are free (:100, as written in the reference).
+    Returns [nopt, evaluated n (ascending), their results] (:159-167)."""
+    import os
     if batchfun is None:
         def batchfun(ns):
             return {n: testfun(n) for n in ns}
-    values = {}
-    to_eval = list(range(liminf, limsup + 1, step))
+    if ncores is None:
+        ncores = (os.cpu_count() or 2) - 1                                 # :17
+    ncores = max(1, int(ncores))
+    values, queued = {}, []
+
+    def launch(k):                                                         # values[[k]] %<-% {testfun(k)}
+        queued.append(k)
+
+    def resolved(k):                                                       # resolved(values)[ind]
+        if queued:
+            values.update(batchfun(list(queued)))
+            del queued[:]
+        return k in values
+
+    to_eval = list(range(liminf, limsup + 1, step))                        # :14
     if to_eval[-1] < limsup:
-        to_eval.append(limsup)                                            # :14-15
-    evalued, nmax = [], []
-    values.update(batchfun(to_eval))
-    downhill = False
-    for k in to_eval:                                                     # :29-83, futures resolving in launch order
-        thisbics = values[k][0]
-        if nmax:
-            testeq = _compare(thisbics, nmax, values, significance, pcrit)
-            nmax = [n for n, t in zip(nmax, testeq) if t in (0, -1)]      # :64
-            if len(nmax) == 0 or min(testeq) >= 0:
-                nmax.append(k)                                            # :65
-        else:
-            nmax = [k]
-        evalued.append(k)
-        if len(nmax) > 0 and len(evalued) >= 3 and sum(1 for e in evalued if e > max(nmax)) >= 2:
-            downhill = True                                               # :81-83 (everything launched is still reported)
-    evalued = sorted(set(to_eval))
-    while step > 1:                                                       # :85-158 refining steps
-        step = int(math.ceil(step / 2.0))
-        cand = sorted(set([n - step for n in nmax] + [n + step for n in nmax]))
-        cand = [c for c in cand if liminf <= c <= limsup and c not in evalued]
-        if cand:
-            values.update(batchfun(cand))
-        for k in cand:
-            thisbics = values[k][0]
-            testeq = _compare(thisbics, nmax, values, significance, pcrit)
-            nmax = [n for n, t in zip(nmax, testeq) if t in (0, -1)]
-            if len(nmax) == 0 or min(testeq) >= 0:
-                nmax.append(k)
+        to_eval.append(limsup)                                             # :15
+    evalued, nmax, downhill = [], [], False                                # :16-19
+    if len(to_eval) > ncores:                                              # :20-26
+        eval_now, eval_latter = to_eval[:ncores], to_eval[ncores:]
+    else:
+        eval_now, eval_latter = list(to_eval), []
+    for k in eval_now:                                                     # :27
+        launch(k)
+    running = list(eval_now)                                               # :28
+    while not downhill and len(running) > 0:                               # :29 large steps, looking for downhill descent
+        still_running = list(running)                                      # :30
+        for k in still_running:                                            # :31
+            if resolved(k):                                                # :33
+                thisbics = values[k][0]                                    # :34
+                if len(nmax) > 0:                                          # :37
+                    nmax = _update_nmax(k, thisbics, nmax, values, significance, pcrit)   # :38-65
+                else:
+                    nmax = [k]                                             # :67
+                running = [r for r in running if r != k]                   # :69
+                evalued.append(k)                                          # :70
+                if len(eval_latter) > 0:                                   # :71-77 start testing another number of signatures
+                    nextrun = eval_latter.pop(0)
+                    launch(nextrun)
+                    running.append(nextrun)
+        if len(nmax) > 0 and len(evalued) >= 3:                            # :80-83 check downhill
+            if sum(1 for e in evalued if e > max(nmax)) >= 2:
+                downhill = True
+    while step > 1:                                                        # :85 refining steps
+        step = int(math.ceil(step / 2.0))                                  # :86
+        to_eval = sorted(set([n - step for n in nmax] + [n + step for n in nmax]))        # :87
+        to_eval = [t for t in to_eval if liminf <= t <= limsup]            # :88
+        to_eval = [t for t in to_eval if t not in evalued and t not in running]           # :89
+        left_eval = len(to_eval)                                           # :90
+        for k in list(running):                                            # :91-97 finished meanwhile: reported, NOT compared
+            if resolved(k):
+                running = [r for r in running if r != k]
+                evalued.append(k)
+        free = ncores - len(running)
+        if left_eval > free:                                               # :98-100, R's 1-based single-element index as written
+            eval_now = [to_eval[free - 1]] if free >= 1 else []
+            eval_latter = to_eval[free:] if free >= 1 else to_eval[1:]     # to_eval[-c(1:free)]; 1:0 is c(1,0): drops the first
+        else:                                                              # :101-104
+            eval_now, eval_latter = list(to_eval), []
+        for k in eval_now:                                                 # :106
+            launch(k)
+        running = running + eval_now                                       # :107
+        while len(eval_now) > 0:                                           # :108
+            still_running = list(eval_now)                                 # :109
+            for k in still_running:                                        # :110
+                if resolved(k):                                            # :112
+                    thisbics = values[k][0]
+                    nmax = _update_nmax(k, thisbics, nmax, values, significance, pcrit)   # :115-139
+                    eval_now = [e for e in eval_now if e != k]             # :141
+                    running = [r for r in running if r != k]               # :142
+                    evalued.append(k)                                      # :143
+                    if len(eval_latter) > 0:                               # :144-150
+                        nextrun = eval_latter.pop(0)
+                        launch(nextrun)
+                        eval_now.append(nextrun)
+    nopt = min(nmax)                                                       # :159 in case of ties, less signatures are better
+    for k in running:                                                      # :160-165
+        if resolved(k):
             evalued.append(k)
-    nopt = min(nmax)                                                      # :159 ties -> fewer signatures
-    evalued = sorted(set(evalued))
-    return [nopt, evalued, [values[n] for n in evalued]]
+    tested = [n for n in range(liminf, limsup + 1) if n in evalued]        # :166
+    return [nopt, tested, [values[n] for n in tested]]                     # :167
 
 
 def batch_bics(M, W, tasks, devices=None):
