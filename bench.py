@@ -19,7 +19,16 @@ One JSON line on stdout (rank 0).  Keys beyond the base contract:
   kernel_ms, kernel_ms_eval   mean launch time of each kernel in burn-in / evaluation sweeps (second and third pass
                    with CUDA events around every launch)
   roofline         dominant kernel z_alloc_fused: algorithmic bytes per launch / mean launch time
-  cpu_baseline     the CPU oracle (oracle/, a port: the reference cannot be built here) on this box
+  cpu_baseline     the reference's src/gibbs_2.cpp (oracle/_ref) -- or the oracle port -- on one host core of this box
+  em_loop          ten reference-shaped calls of 200 burn-in + 100 evaluation sweeps with keep_par=TRUE, each fed the
+                   previous call's last samples (the EM loop of R/cpp_eBayesNMF.R:104-152 as R drives it), host arrays
+  nsig             the second half of BASELINE.json's metric: wall time of the model-selection sweep nsig = 2..20 x 4
+                   chains, 1000 + 1000 sweeps each (R/signeR.R:66), on the same cohort, over the N ranks (strong scaling)
+  sharded          BASELINE.json config 4 (1536 x 20,000, K = 30): ONE chain with its genome columns sharded over the
+                   N GPUs, driven by rank 0 (ms per sweep), plus a small sharded chain over the same devices checked
+                   bit for bit against the oracle (sharded_parity_ok; NCCL when N > 1, emulated shards when N = 1)
+Timing: whatever --warmup says, at least 200 untimed sweeps precede the timed region (a 5-sweep warm-up leaves the
+L2 / instruction caches and clocks cold: 19 % slower sweeps); --steps stays the timed count.
 """
 import argparse
 import json
@@ -35,6 +44,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG", "NONE")      # keep stdout to the one JSON line (no NCCL version banner)
 
+MIN_WARMUP_SWEEPS = 200          # untimed, whatever --warmup says (see the docstring)
 METRIC = "gibbs_sweeps_per_s"
 UNIT = "sweeps/s"
 WORKLOADS = {
@@ -43,6 +53,13 @@ WORKLOADS = {
     "cfg5_96x100000": dict(K=40, desc="synthetic 96x100000 genomes, K=40"),
     "cfg4_1536x20000_K30": dict(K=30, desc="synthetic 1536x20000, K=30"),
 }
+
+
+def config_dict(workload, I, J, K):
+    """identical in both arms (the driver compares them)"""
+    return dict(workload=workload, description=WORKLOADS[workload]["desc"], I=I, J=J, K=K, chains_per_gpu=1,
+                l2="no flush between steps: a chain iterates over the same cohort every sweep, its working set (M int32 + W f64 "
+                   "= 11.5 MB, state 5 MB) is L2-resident by design")
 
 
 def peaks():
@@ -184,7 +201,7 @@ def run_reference(args, rank, world):
               "value scaled by %d/%d to the full cohort" % (Js, J, Js, J))
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step_sample * (J / Js), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic", config=dict(workload=args.workload, description=WORKLOADS[args.workload]["desc"], I=I, J=J, K=K),
+                data="synthetic", config=config_dict(args.workload, I, J, K),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -257,6 +274,113 @@ def run_sharded(args):
                           call_seconds=dt, upload_and_setup_seconds=dt - loop_ms * 1e-3, zin_total=int(r.Zin.sum()), m_total=int(M.sum()))), flush=True)
 
 
+def leg_em_loop(sg, M, W, st, hyper, Z0, local, calls=10, burn=200, ev=100):
+    """The EM loop as R drives it through the drop-in boundary (R/cpp_eBayesNMF.R:104-152): every iteration is one
+    stateless GibbsSamplerCpp(..., burn=200, eval=EM_eval_it=100, keep_par=TRUE) with host arrays, and the next one
+    starts from the last samples of Zs, Ps, Es, Aps, Bps, Aes, Bes it returned (:108-139)."""
+    P, E, Ap, Bp, Ae, Be = (st[k] for k in ("P", "E", "Ap", "Bp", "Ae", "Be"))
+    Z = Z0
+    sg.GibbsSamplerCpp(M, W, Z, P, E, Ap, Bp, Ae, Be, *hyper, 3, 3, False, False, False, False, True, seed=40, device=local)
+    t0 = time.perf_counter()
+    for it in range(calls):
+        r = sg.GibbsSamplerCpp(M, W, Z, P, E, Ap, Bp, Ae, Be, *hyper, burn, ev, False, False, False, False, True, seed=41 + it,
+                               device=local)
+        Z = r[0][:, :, :, 0]
+        P, E, Ap, Bp, Ae, Be = r[2][:, :, -1], r[3][:, :, -1], r[4][:, :, -1], r[5][:, :, -1], r[6][:, :, -1], r[7][:, :, -1]
+    dt = time.perf_counter() - t0
+    I, J = M.shape
+    K = P.shape[1]
+    per_call_h2d = 8.0 * (2 * I * J + I * J * K + 3 * (I * K + K * J))
+    per_call_d2h = 8.0 * (I * J * K + ev * 3 * (I * K + K * J))
+    return dict(calls=calls, burn=burn, eval=ev, keep_par=True, seconds=dt, seconds_per_call=dt / calls,
+                sweeps_per_s=calls * (burn + ev) / dt, h2d_bytes_per_call=per_call_h2d, d2h_bytes_per_call=per_call_d2h,
+                call="GibbsSamplerCpp(..., burn=200, eval=100, keep_par=TRUE) x %d, state fed back through host arrays "
+                     "(R/cpp_eBayesNMF.R:104-152)" % calls)
+
+
+def leg_nsig(M, W, local, lo=2, hi=20, chains=4, burn=1000, ev=1000):
+    """nsig = lo..hi x `chains` chains, `burn` + `ev` sweeps each (R/signeR.R:66, be/sqrt(n) :163), dealt longest-first
+    over the ranks (one process per GPU, no data-path collective; only BIC vectors travel).  Returns the wall time
+    (max over ranks) and the BIC-optimal nsig."""
+    from signer_b200 import dist as sgdist, synth
+    from signer_b200.signer import batch_bics
+    I, J = M.shape
+    h0 = synth.hyper_tuple()
+    tasks = []
+    for n in range(lo, hi + 1):
+        for c in range(chains):
+            h = list(h0); h[3] = h0[3] / np.sqrt(n)
+            tasks.append(dict(K=n, state=synth.init_state(I, J, n, hyper=dict(be=h[3]), seed=1000 * n + c), hyper=tuple(h),
+                              burn=burn, eval=ev, seed=1000 * n + c))
+
+    def runner(ts):
+        return batch_bics(M, W, ts, devices=[local]) if ts else []
+    sgdist.barrier()
+    t0 = time.perf_counter()
+    res = sgdist.run_tasks_distributed(tasks, runner)
+    sgdist.barrier()
+    dt = sgdist.max_over_ranks(time.perf_counter() - t0)
+    med = {}
+    for tk, (ll, bic) in zip(tasks, res):
+        med.setdefault(tk["K"], []).append(float(np.median(bic)))
+    med = {k: float(np.mean(v)) for k, v in med.items()}
+    best = max(sorted(med), key=lambda k: med[k])
+    return dict(nsig_wall_s=dt, bic_optimal_nsig=best, nsig=[lo, hi], chains=chains, burn=burn, eval=ev, tasks=len(tasks),
+                sweeps_per_s=sum(t["burn"] + t["eval"] for t in tasks) / dt, scaling="strong",
+                median_bic={str(k): v for k, v in sorted(med.items())})
+
+
+def leg_sharded(n_dev, steps=20):
+    """Rank 0 only.  (a) BASELINE.json config 4 (1536 x 20,000, K = 30): one chain, genome columns sharded over n_dev
+    GPUs through signer_gibbs_run_sharded; ms per sweep from the library's own clock around the sweep loop.
+    (b) a small sharded chain over the same devices (real NCCL when n_dev > 1; two emulated shards on the one GPU
+    otherwise) compared bit for bit with the oracle run with the same number of shards -- the oracle is the checker
+    here, never the thing measured."""
+    import signer_b200 as sg
+    from signer_b200 import _lib, synth
+    wl = "cfg4_1536x20000_K30"
+    K = WORKLOADS[wl]["K"]
+    M, W, _, _ = synth.named(wl)
+    I, J = M.shape
+    st = synth.init_state(I, J, K, seed=4)
+    h = synth.hyper_tuple()
+    devs = list(range(n_dev))
+    a = (st["P"], st["E"], st["Ap"], st["Bp"], st["Ae"], st["Be"], *h)
+    sg.GibbsSamplerCpp(M, W, None, *a, 3, 0, False, False, False, False, False, seed=1, shard_devices=devs)     # warm-up
+    t0 = time.perf_counter()
+    r = sg.GibbsSamplerCpp(M, W, None, *a, steps, 0, False, False, False, False, False, seed=1, shard_devices=devs)
+    dt = time.perf_counter() - t0
+    loop_ms = float(_lib.lib().signer_last_loop_ms())
+    out = dict(workload=wl, I=I, J=J, K=K, shards=n_dev, steps=steps, sharded_ms_per_sweep=loop_ms / steps,
+               sharded_sweeps_per_s=steps / (loop_ms * 1e-3), call_seconds=dt, scaling="strong",
+               checksum_ok=bool(int(r.Zin.sum()) == int(np.trunc(M).sum())),
+               exchange="per sweep: Zin (int32, I*K) all-reduce + W E' (f64, I*K per shard) all-gather over NVLink" if n_dev > 1 else "none (one shard)")
+    del M, W, r
+    # (b) parity on a small cohort, all outputs
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import compare_all
+    pdevs = devs if n_dev > 1 else [0, 0]
+    I2, J2, K2 = 24, 128 * 9 + 17, 5
+    M2, W2, _, _ = synth.cohort(I2, J2, K2, burden=25.0 * I2, seed=J2)
+    M2[1, 3] = 4000.0
+    st2 = synth.init_state(I2, J2, K2, seed=5)
+    got = sg.GibbsSamplerCpp(M2, W2, None, st2["P"], st2["E"], st2["Ap"], st2["Bp"], st2["Ae"], st2["Be"], *h, 10, 5,
+                             False, False, False, False, True, seed=9, shard_devices=pdevs)
+    hd = dict(zip(("ap", "bp", "ae", "be", "lp", "le", "var_ap", "var_ae"), h))
+    want = O.gibbs_run(M2, W2, None, st2["P"], st2["E"], st2["Ap"], st2["Bp"], st2["Ae"], st2["Be"], hyper=hd, burn=10, eval=5,
+                       keep_par=True, seed=9, nshards=len(pdevs))
+    try:
+        compare_all(got, want)
+        out["sharded_parity_ok"] = True
+    except AssertionError as e:
+        out["sharded_parity_ok"] = False
+        out["sharded_parity_error"] = str(e)[:300]
+    out["sharded_parity_case"] = "%dx%d K=%d, 10+5 sweeps, %d shards %s, every output bit for bit against the oracle" % (
+        I2, J2, K2, len(pdevs), "over NCCL" if n_dev > 1 else "emulated on one GPU")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +391,7 @@ def main():
                     help="default: cfg3_96x10000_K20 (sweeps), cfg2_96x560 (nsig), cfg4_1536x20000_K30 (sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the em_loop, nsig and sharded legs (kernel work: faster turn-around)")
     ap.add_argument("--mode", default="sweeps", choices=["sweeps", "nsig", "sharded"],
                     help="nsig: wall time of a full nsig model-selection sweep (secondary metric of BASELINE.json)")
     ap.add_argument("--nsig-range", default="2,10")
@@ -316,7 +441,7 @@ def main():
     chain.set_stream(stream.cuda_stream)
 
     # ---------------- value: burn-in sweeps, device resident
-    chain.run(burn=args.warmup, fetch=False)
+    chain.run(burn=max(args.warmup, MIN_WARMUP_SWEEPS), fetch=False)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -419,6 +544,26 @@ def main():
                    median_bic=float(np.median(res.bic)))
         del res
 
+    # ---------------- extras: the EM-shaped loop, the nsig sweep and the column-sharded chain (docstring)
+    em = nsig = sharded = None
+    if not args.no_extras and args.workload == "cfg3_96x10000_K20":
+        if rank == 0 and not args.no_e2e:
+            em = leg_em_loop(sg, M, W, st, hyper, Z0, local)
+        chain.close()
+        sg.release_caches()
+        nsig = leg_nsig(M, W, local)
+        # rank 0 drives all N devices; the other ranks wait on the HOST (a gloo barrier): an NCCL barrier would park a
+        # spinning kernel on the very GPUs the sharded chain needs
+        cpu_group = dist.new_group(backend="gloo") if dist_on else None
+        if rank == 0:
+            try:
+                sharded = leg_sharded(world)
+            except Exception as e:                      # keep the headline line even if this leg fails
+                sharded = dict(error=str(e)[:300])
+            sg.release_caches()
+        if dist_on:
+            dist.barrier(group=cpu_group)
+
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -429,9 +574,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
-                    config=dict(workload=args.workload, description=wl["desc"], I=I, J=J, K=K, chains_per_gpu=1,
-                                l2="working set (M int32 + W f64 = 11.5 MB, state 5 MB) is L2-resident by design: a chain "
-                                   "iterates over the same cohort every sweep, so no L2 flush between steps"),
+                    config=config_dict(args.workload, I, J, K),
                     clocks=clk, e2e=e2e, gpu_launches=int(launches) * world,
                     eval_value=eval_value, eval_ms_per_step=ms_eval / n_eval,
                     roofline=roofline,
@@ -447,7 +590,11 @@ def main():
                                      step1_fraction_of_ceiling=(n_cat + n_bin) / n_cnt / (z_ms * 1e-3) / ceil.value,
                                      note="ceiling: Philox4x32-10 + 32-bit uniform + one inversion step per lane, no memory (signer_draw_ceiling); "
                                           "fraction = step-1 draws per second of z_alloc_fused time / ceiling"),
-                    cpu_baseline=cpu)
+                    cpu_baseline=cpu, em_loop=em, nsig=nsig, sharded=sharded)
+        if nsig:
+            line["nsig_wall_s"] = nsig["nsig_wall_s"]; line["bic_optimal_nsig"] = nsig["bic_optimal_nsig"]
+        if sharded and "sharded_ms_per_sweep" in sharded:
+            line["sharded_ms_per_sweep"] = sharded["sharded_ms_per_sweep"]; line["sharded_parity_ok"] = sharded.get("sharded_parity_ok")
         print(json.dumps(line), flush=True)
     chain.close()
     if dist_on:

@@ -7,13 +7,13 @@
 // unchanged, and returns the same positional list (src/gibbs_2.cpp:406-423) with the same named
 // dim attributes (cube_to_rcpp, src/gibbs_2.cpp:72-82) -- R code indexes Ps[,,'r'=r].
 //
-// NOT COMPILED OR RUN IN THIS REPOSITORY'S CI: neither this image nor the GPU box has R, Rcpp or
-// RcppArmadillo.  tests/ drive the same C ABI through signer_b200/gibbs.py instead.
+// R, Rcpp and RcppArmadillo are absent from this image and from the GPU box, so the file cannot be built into the
+// package here.  It IS compiled, unmodified, against a stand-in Rcpp.h (oracle/r_stub, test infrastructure) and its
+// entry point is executed on the GPU by tests/test_gpu_rshim.py, which compares the returned list with the one the
+// reference's own src/gibbs_2.cpp returns on the same inputs (oracle/_ref).
 //
-// Build inside the package:  src/Makevars
-//     PKG_CPPFLAGS = -I$(SIGNER_B200)/include
-//     PKG_LIBS = -L$(SIGNER_B200)/signer_b200 -lsigner_gibbs -Wl,-rpath,$(SIGNER_B200)/signer_b200
-// (src/fuzzy.cpp and its registration stay as they are.)
+// Build inside the package: r_shim/Makevars replaces src/Makevars (src/fuzzy.cpp and the registration in
+// src/signeR_init.c stay as they are).
 #include <Rcpp.h>
 #include "signer_gibbs.h"
 

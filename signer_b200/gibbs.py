@@ -41,6 +41,11 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(dp)
 
 
+def release_caches():
+    """signer_release_caches(): drop the cached cohorts, trim the device memory pools, free the cached pinned buffers."""
+    _lib.lib().signer_release_caches()
+
+
 class SampleList(list):
     """The reference's 8-slot return list plus what the device computed on the way
     (log-likelihoods, BICs, final state, final Z statistics)."""

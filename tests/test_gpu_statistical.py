@@ -13,6 +13,19 @@ COS_MIN = 0.99
 EXPO_REL_ERR_MAX = 0.05
 
 
+def _report(**kw):
+    """numbers worth reading after a GPU run (gpurun_out/ comes back from the box)"""
+    import json, os
+    print("statistical report:", json.dumps(kw))
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "statistical_report.jsonl"), "a") as f:
+            f.write(json.dumps(kw) + "\n")
+    except OSError:
+        pass
+
+
 def _planted(I=96, J=240, K=4, seed=5):
     M, W, Pt, Et = synth.cohort(I, J, K, burden=4000.0, seed=seed)
     return M, W, Pt, Et
@@ -33,11 +46,18 @@ def test_posterior_matches_numpy_oracle(sg):
     Pr, Er = NG.summaries(ref["Ps"], ref["Es"])
     perm, cos = NG.match_signatures(Pg, Pr)
     assert cos.min() >= COS_MIN, cos
-    # exposures: compare on the entries that carry signal (>= 5 % of the genome's total)
+    # exposures: BASELINE.json's tolerance, median relative error <= 5 %, over ALL K x J entries (no filter) ...
     Er_m = Er[perm, :]
+    rel_all = np.abs(Eg - Er_m) / Eg
+    med_all = float(np.median(rel_all))
+    # ... and on the entries that carry signal (>= 5 % of the genome's total), where Monte Carlo noise of the two
+    # 400-sample medians matters least
     big = Eg >= 0.05 * Eg.sum(axis=0, keepdims=True)
-    rel = np.abs(Eg - Er_m)[big] / Eg[big]
-    assert np.median(rel) <= EXPO_REL_ERR_MAX, np.median(rel)
+    med_big = float(np.median(rel_all[big]))
+    _report(exposure_median_rel_err_unfiltered=med_all, exposure_median_rel_err_signal_entries=med_big,
+            signature_cosine_min=float(cos.min()))
+    assert med_all <= EXPO_REL_ERR_MAX, med_all
+    assert med_big <= EXPO_REL_ERR_MAX, med_big
     # both recover the planted signatures
     _, cos_t = NG.match_signatures(Pg, Pt)
     assert cos_t.min() >= 0.97, cos_t
@@ -77,6 +97,7 @@ def test_ebayesnmf_and_model_selection_breast21(sg):
     med = [float(np.median(b)) for b in res["Test_BICs"]]
     nopt = res["Nsign"]
     assert nopt == res["tested_n"][int(np.argmax(med))]           # plain argmax of the median BIC agrees with the replayed rule
+    _report(breast21_nopt=int(nopt), breast21_median_bics=med)
     assert 3 <= nopt <= 7, (nopt, med)
     assert med[res["tested_n"].index(nopt)] > med[0]
     Phat, Ehat = res["Phat"], res["Ehat"]
