@@ -34,7 +34,7 @@ extern "C" {
 
 #define SIGNER_ABI_VERSION 3
 /* Version of the draw specification: the same seed gives the same chain only within one version. */
-#define SIGNER_DRAW_SPEC_VERSION 6
+#define SIGNER_DRAW_SPEC_VERSION 7
 
 /* status codes */
 enum {
@@ -154,7 +154,7 @@ int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W,
                        signer_task *tasks, int32_t n_tasks,
                        const int32_t *devices, int32_t n_devices);
 
-/* One chain over several GPUs, the genome columns sharded in 128-genome segments (very wide cohorts, BASELINE.json
+/* One chain over several GPUs, the genome columns sharded in 32-genome segments (very wide cohorts, BASELINE.json
  * config 4).  P, Ap, Bp are replicated; per sweep the shards exchange two sets of I*K values (NCCL all-reduce over
  * NVLink): the integer sums over genomes of Z and their ordered W E' sums.  Same arguments and outputs as
  * signer_gibbs_run (opts.device ignored).  devices: n_devices distinct CUDA ordinals, or the same ordinal repeated

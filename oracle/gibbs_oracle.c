@@ -22,13 +22,13 @@
  *       k order, zero-probability skip, pp<1 test, early exit at n<=0, remainder to the last class.
  *
  * What it does NOT reproduce: R's RNG stream and R's rbinom/rgamma algorithms (unavailable).
- * Instead every random draw follows the "draw specification v6" below: counter-based
+ * Instead every random draw follows the "draw specification v7" below: counter-based
  * Philox4x32-10 streams addressed by (seed, sweep, step, element, block) and samplers built only
  * from IEEE-754 correctly rounded operations (+ - * / sqrt fma) in a fixed order, so that an
  * independent implementation (the CUDA kernels) can be compared BIT FOR BIT.
  * Compile with -ffp-contract=off (see oracle/Makefile); every fused multiply-add is explicit.
  *
- * Draw specification v6 (shared contract with signer_b200/csrc, written independently there):
+ * Draw specification v7 (shared contract with signer_b200/csrc, written independently there):
  *   stream address: key = (seed_lo, seed_hi); counter = (block, element, stream_id, sweep)
  *   stream ids: 0 permutation, 1..7 Gibbs steps, 8 initial Z
  *   element: step 1/8: i + I*j ; P family (2,4,6): i + I*k ; E family (3,5,7): k + K*j
@@ -53,8 +53,9 @@
  *                block 0xFFFFFFFF gives (boost uniform for shape<1, MH acceptance uniform)
  *   log:         table-driven, division-free (det_tables.h), see oracle_log; exp: fdlibm-style; lgamma: shift to
  *                >= 8 + 8 Stirling terms
- *   fp reductions: PE = fma chain over k; corrP = fma chain over i; corrE = 128-column segment
- *                  fma chains, segments added in ascending order (per shard, shards ascending);
+ *   fp reductions: PE = fma chain over k; corrP = fma chain over i; corrE = fma chains over segments of 32 genomes,
+ *                  the segment sums added in blocks of 32 (sequentially inside a block; the block sums form the
+ *                  next level) per shard, the shard sums likewise;
  *                  loglik = per-column sums in 32-row chunks (chunks added in order), then a
  *                  stride-halving tree over the zero-padded column array.
  */
@@ -65,7 +66,8 @@
 
 #include "det_tables.h"
 
-#define ORACLE_SEG 128
+#define ORACLE_SEG 32
+#define ORACLE_SUMBLK 32
 #define ORACLE_LLCHUNK 32
 #define BINV_MAX 30.0
 #define TINY 1e-160
@@ -562,28 +564,48 @@ static void cube_sum_i_t(const chain *c, double *Znj /* K x J */)
         Znj[k + (size_t)c->K * j] += c->Z[ZIDX(c, i, j, k)];
 }
 
-/* corrE = W * E.t()  (src/gibbs_2.cpp:111) with the specified summation order. */
+/* Ordered sum of a[0..n) in blocks of ORACLE_SUMBLK: every block of consecutive entries is added sequentially (from 0.0),
+ * the block sums form the next level, until one value is left.  Overwrites a. */
+static double blocked_sum(double *a, int n)
+{
+    if (n <= 0) return 0.0;
+    for (;;) {
+        int nb = (n + ORACLE_SUMBLK - 1) / ORACLE_SUMBLK;
+        for (int b = 0; b < nb; b++) {
+            int t1 = (b + 1) * ORACLE_SUMBLK; if (t1 > n) t1 = n;
+            double sacc = 0.0;
+            for (int t = b * ORACLE_SUMBLK; t < t1; t++) sacc = sacc + a[t];
+            a[b] = sacc;
+        }
+        if (nb == 1) return a[0];
+        n = nb;
+    }
+}
+
+/* corrE = W * E.t()  (src/gibbs_2.cpp:111) with the specified summation order: fma chains over segments of
+ * ORACLE_SEG genomes; per shard the segment sums are added by blocked_sum; the shard sums likewise. */
 static void corr_E(const chain *c, double *corrE /* I x K */)
 {
     int I = c->I, J = c->J, K = c->K;
     int nseg = (J + ORACLE_SEG - 1) / ORACLE_SEG;
     int nsh = c->nshards < 1 ? 1 : c->nshards;
+    double *part = malloc(sizeof(double) * (nseg + 1)), *tot = malloc(sizeof(double) * (nsh + 1));
     for (int i = 0; i < I; i++) for (int k = 0; k < K; k++) {
-        double tot = 0.0;
         for (int sh = 0; sh < nsh; sh++) {
             /* shard sh owns segments [sh*nseg/nsh, (sh+1)*nseg/nsh) */
             int s0 = (int)((long long)sh * nseg / nsh), s1 = (int)((long long)(sh + 1) * nseg / nsh);
-            double part = 0.0;
+            int np = 0;
             for (int sg = s0; sg < s1; sg++) {
                 int j0 = sg * ORACLE_SEG, j1 = j0 + ORACLE_SEG; if (j1 > J) j1 = J;
                 double acc = 0.0;
                 for (int j = j0; j < j1; j++) acc = fma(c->W[i + (size_t)I * j], c->E[k + (size_t)K * j], acc);
-                part = part + acc;
+                part[np++] = acc;
             }
-            tot = tot + part;
+            tot[sh] = blocked_sum(part, np);
         }
-        corrE[i + (size_t)I * k] = tot;
+        corrE[i + (size_t)I * k] = blocked_sum(tot, nsh);
     }
+    free(part); free(tot);
 }
 
 /* step 2 -- src/gibbs_2.cpp:106-120 */

@@ -6,8 +6,8 @@
 //   * arma::mat / cube / rowvec / Col<int> / Row<int> with eager element-wise arithmetic
 //     (each operator is one correctly rounded fp64 operation per element, evaluated in C++'s
 //     left-to-right order like Armadillo's expression templates evaluate per element);
-//   * matrix products with the summation orders of the draw specification (W*E.t(): 128-column
-//     segment fma chains; P.t()*W and P*E: fma chains);
+//   * matrix products with the summation orders of the draw specification (W*E.t(): 32-column
+//     segment fma chains, blocked sums; P.t()*W and P*E: fma chains);
 //   * R::rmultinom, R::rgamma, arma::shuffle, arma::randu, arma::log/exp/lgamma routed to the
 //     draw specification (oracle/gibbs_oracle.c) through a replay context that addresses every
 //     call by (sweep, step, element) exactly as the reference's loops visit them;
@@ -113,19 +113,31 @@ inline mat operator*(const mat &a, const mat &b) {               // P*E, P.col(m
     }
     return r;
 }
-inline mat operator*(const mat &a, const trans_view &bt) {       // W * E.t(): 128-column segment fma chains, segments ascending
+inline mat operator*(const mat &a, const trans_view &bt) {       // W * E.t(): fma chains over 32-column segments, segment sums added in blocks of 32
     const mat &b = bt.m;
     if (a.n_cols != b.n_cols) throw std::runtime_error("arma shim: product size mismatch");
     mat r(a.n_rows, b.n_rows);
+    std::vector<double> part;
     for (uword i = 0; i < a.n_rows; i++) for (uword k = 0; k < b.n_rows; k++) {
-        double part = 0.0;
-        for (uword j0 = 0; j0 < a.n_cols; j0 += 128) {
-            uword j1 = j0 + 128 < a.n_cols ? j0 + 128 : a.n_cols;
+        part.clear();
+        for (uword j0 = 0; j0 < a.n_cols; j0 += 32) {
+            uword j1 = j0 + 32 < a.n_cols ? j0 + 32 : a.n_cols;
             double acc = 0.0;
             for (uword j = j0; j < j1; j++) acc = std::fma(a(i, j), b(k, j), acc);
-            part = part + acc;
+            part.push_back(acc);
         }
-        r(i, k) = 0.0 + part;
+        uword n = part.size();
+        while (n > 1) {                                          // draw specification v7: blocked ordered sum
+            uword nb = (n + 31) / 32;
+            for (uword bb = 0; bb < nb; bb++) {
+                uword t1 = (bb + 1) * 32 < n ? (bb + 1) * 32 : n;
+                double sacc = 0.0;
+                for (uword t = bb * 32; t < t1; t++) sacc = sacc + part[t];
+                part[bb] = sacc;
+            }
+            n = nb;
+        }
+        r(i, k) = 0.0 + (n ? 0.0 + part[0] : 0.0);
     }
     return r;
 }

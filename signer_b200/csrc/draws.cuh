@@ -1,4 +1,4 @@
-// draws.cuh -- device primitives of the draw specification v6.
+// draws.cuh -- device primitives of the draw specification v7.
 //
 // Everything here is built from IEEE-754 correctly rounded fp64 operations (+ - * / sqrt fma) in
 // a fixed order, plus integer arithmetic, so that results are bit-identical to any other
@@ -23,7 +23,7 @@ constexpr double kTiny = 1e-160;              // pow(10,-160) clamps, src/gibbs_
 constexpr double kBinvMax = 30.0;             // n*p below this: inversion (as R's rbinom); otherwise BTRS
 constexpr uint32_t kAuxBlock = 0xFFFFFFFFu;   // block holding (boost uniform, MH uniform)
 constexpr uint32_t kBtrsBlock0 = 0x1000u;     // first BTRS block of a step-1 stream
-constexpr int kSeg = 128;                     // columns per corrE segment
+constexpr int kSeg = 32;                      // genomes per W E' segment (draw specification v7)
 
 enum Stream : uint32_t { kStPerm = 0, kStZ = 1, kStP = 2, kStE = 3, kStBp = 4, kStBe = 5, kStAp = 6, kStAe = 7, kStZinit = 8 };
 
@@ -273,7 +273,7 @@ __device__ const double g_zig_x[129] = SG_ZIG_X;
 __device__ const double g_zig_ratio[128] = SG_ZIG_RATIO;
 constexpr uint32_t kNormBlock0 = 0x10000u;
 
-__device__ __noinline__ double normal_slow(const UStream &s, uint32_t t, U4 w)
+__device__ __noinline__ double normal_slow(const UStream s, uint32_t t, U4 w)
 {
     uint32_t q = 0;
     for (;;) {
@@ -316,7 +316,7 @@ SG_D double normal_draw(const UStream &s, uint32_t t, const U4 &w)
 // ---------------------------------------------------------------- gamma (Marsaglia & Tsang 2000)
 // Gamma(shape, rate) with one_gamma_dist's clamps (src/gibbs_2.cpp:39-43).  Attempt t reads block t: the normal
 // from words 0,1 (normal_draw), the acceptance uniform from words 2,3.
-__device__ __noinline__ double gamma_draw(const UStream &s, double shape, double rate)
+__device__ __noinline__ double gamma_draw(const UStream s, double shape, double rate)
 {
     const double a = (kTiny < shape) ? shape : kTiny;
     const double invr = 1.0 / rate;

@@ -23,7 +23,6 @@ namespace sg {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-constexpr int kEThreads = 256;    // e_family: 128 genomes x 2 class pairs
 constexpr int kLLChunk = 32;      // rows per log-likelihood chunk
 
 struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
@@ -199,6 +198,19 @@ __device__ unsigned long long g_z_phase[2][8];      // [small/large][phase] warp
 #define SG_ZCLK(ph)
 #endif
 
+SG_D void sg_prefetch(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+// The constant tables of the elementary functions (log: 2 KB, ziggurat: 2 KB) live in global memory; L1 does not keep
+// them across kernels, and in a small latency-bound kernel every det_log would start with an L2 round trip in the middle
+// of a dependent chain.  The first 33 threads of a block pull the lines into L1 while the block does something else.
+SG_D void prefetch_tables(int t)
+{
+    if (t < 0) return;
+    if (t < 16) sg_prefetch(reinterpret_cast<const char *>(g_log_tab) + 128 * t);
+    else if (t < 25) sg_prefetch(reinterpret_cast<const char *>(g_zig_x) + 128 * (t - 16));
+    else if (t < 33) sg_prefetch(reinterpret_cast<const char *>(g_zig_ratio) + 128 * (t - 25));
+}
+
 SG_D int z_expo(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
 __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParams p)
@@ -285,7 +297,10 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                 c = c + q0;
                 buf[k * 32] = bycount_small ? c : q0;
             }
-            if (bycount_small) for (k = K - 1; k < R; ++k) buf[k * 32] = kInf;   // c_{K-1} is not a threshold
+            // c_{K-1} is not a threshold.  A lane on the chain path keeps its K products but takes part in the warp's direct
+            // draws with x < 0: its rows beyond K must not hold left-over shared memory (a garbage value <= x would send
+            // the search past the lane's column)
+            for (k = bycount_small ? K - 1 : K; k < R; ++k) buf[k * 32] = kInf;
         }
         // a batch of small counts: its claim has come back by now; fetch the next batch's list entries while this
         // one draws
@@ -293,7 +308,15 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
         if (early) {
             nxt = __shfl_sync(kFull, pend, 0);
             const int cell = nxt * 32 + lane;
-            if (nxt < p.n_batches && cell < p.n_cells) { n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell]; }
+            if (nxt < p.n_batches && cell < p.n_cells) {
+                n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell];
+#ifndef SG_Z_NO_PREFETCH
+                // the next batch's columns of E (cells of one round class are listed genome-major: a few distinct
+                // columns per warp) travel from L2 to L1 while this batch draws
+                const char *en = reinterpret_cast<const char *>(p.E + (size_t)K * col_nxt);
+                sg_prefetch(en); sg_prefetch(en + 8 * K - 8);
+#endif
+            }
         }
         SG_ZCLK(1)                                          // staging
         const bool ok = (S > 0.0 && S <= 1.7976931348623157e308);
@@ -423,8 +446,6 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
 // element-wise updates shared by the two families
 // ------------------------------------------------------------------------------------------------
 // steps 4/5 (src/gibbs_2.cpp:140-169)
-SG_D void sg_prefetch(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-
 SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double a, double b)
 {
     UStream us; us.init(key, sweep, stream, e);
@@ -485,14 +506,71 @@ struct Ops {
 };
 
 // ------------------------------------------------------------------------------------------------
-// KP  p_family : gibbs_step2/4/6 (src/gibbs_2.cpp:106-120,140-153,172-210) on I x K
+// Ordered sum of a[0..n) for 32 consecutive elements e0 .. e0+31 (entry t of element e at a[t * stride + e]) by one
+// block, draw specification v7: blocks of kSumBlk consecutive entries are added sequentially (from 0.0), the block
+// sums form the next level, until one value is left.  Level 1 reads global memory: warp w takes the blocks w, w + 8,
+// ..., lane = element, so every load is a coalesced row of 32 elements and a thread has 16 of them in flight.  The
+// upper levels are a handful of adds per element in shared memory (lvl: [32][n1p], n1p = blocked_sum_pitch(n)).
+// Call with all threads of the block; threads 0..31 get their element's total.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSumBlk = 32;
+constexpr int kPWarps = 8, kPElems = 32;
+__host__ __device__ inline int sum_blocks(int n) { return (n + kSumBlk - 1) / kSumBlk; }
+__host__ __device__ inline int blocked_sum_pitch(int n) { return sum_blocks(n) | 1; }
+__host__ __device__ inline size_t blocked_sum_smem_bytes(int n) { return sizeof(double) * kPElems * (size_t)blocked_sum_pitch(n); }
+
+SG_D double blocked_sum_block(const double *a, int n, size_t stride, size_t e0, size_t n_elems, double *lvl)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n1 = sum_blocks(n), n1p = blocked_sum_pitch(n);
+    const size_t e = e0 + lane;
+    if (e < n_elems) {
+        for (int b = warp; b < n1; b += kPWarps) {
+            const int t0 = b * kSumBlk, cnt = min(kSumBlk, n - t0);
+            const double *q = a + (size_t)t0 * stride + e;
+            double v[16], sacc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (u < cnt) ? q[(size_t)u * stride] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) if (u < cnt) sacc = sacc + v[u];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (16 + u < cnt) ? q[(size_t)(16 + u) * stride] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) if (16 + u < cnt) sacc = sacc + v[u];
+            lvl[lane * n1p + b] = sacc;
+        }
+    }
+    __syncthreads();
+    double tot = 0.0;
+    if (tid < kPElems && e < n_elems && n > 0) {
+        double *row = lvl + tid * n1p;
+        int m = n1;
+        while (m > 1) {                                    // in place: block b is written after everything it covers was read
+            const int nb = sum_blocks(m);
+            for (int b = 0; b < nb; ++b) {
+                const int t0 = b * kSumBlk, cnt = min(kSumBlk, m - t0);
+                double sacc = 0.0;
+                for (int u = 0; u < cnt; ++u) sacc = sacc + row[t0 + u];
+                row[b] = sacc;
+            }
+            m = nb;
+        }
+        tot = row[0];
+    }
+    return tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KP  p_family : gibbs_step2/4/6 (src/gibbs_2.cpp:106-120,140-153,172-210) on I x K.
+// A block owns 32 elements.  When step 2 runs, the whole block first adds the W E' segment sums of its elements in the
+// specified order (blocked_sum_block); then warp 0 applies the steps of this sweep, one element per lane.
 // ------------------------------------------------------------------------------------------------
 struct PParams {
     int IK;
     double *P, *Ap, *Bp;
     const int *Zin;
-    const double *corrE_part;   // [n_seg][I*K] segment partials of W E'
-    int n_seg, n_shards;
+    const double *corrE_part;   // [n_part][I*K]: segment sums of W E' (unsharded) or the shards' ordered sums (sharded)
+    int n_part;
     double *Ps_slot, *Aps_slot, *Bps_slot;   // sample slots or null (src/gibbs_2.cpp:325-333)
     ACache acache;
     Hyper h;
@@ -501,47 +579,30 @@ struct PParams {
     Ops ops;
 };
 
-#ifdef SG_Z_TIMING      // experiments only: clocks of thread 0 of each block of the last p_family launch
-__device__ long long g_p_clock[64][8];
-#define SG_PCLK(slot) if (threadIdx.x == 0 && blockIdx.x < 64) g_p_clock[blockIdx.x][slot] = clock64();
-#else
-#define SG_PCLK(slot)
-#endif
-
-__global__ void __launch_bounds__(128) p_family(const PParams p)
+__global__ void __launch_bounds__(32 * kPWarps) p_family(const PParams p)
 {
-    SG_PCLK(0)
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.IK) return;
+    extern __shared__ __align__(16) double p_smem[];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * kPElems;
+    bool has2 = false;
+    for (int o = 0; o < p.ops.n; ++o) has2 |= (p.ops.get(o) == 2);
+    double corrE = 0.0;
+    prefetch_tables(tid - 32);                              // warps 1 and 2, while warp 0 starts on its state
+    const int e = e0 + tid;
+    const bool mine = tid < kPElems && e < p.IK;
+    if (mine) {                                             // what the element updates will want, on its way before the sums
+        sg_prefetch(p.P + e); sg_prefetch(p.Ap + e); sg_prefetch(p.Bp + e); sg_prefetch(p.Zin + e);
+        sg_prefetch(p.acache.lg1 + e); sg_prefetch(p.acache.lg2 + e); sg_prefetch(p.acache.lg + e);
+    }
+    if (has2) corrE = blocked_sum_block(p.corrE_part, p.n_part, (size_t)p.IK, (size_t)e0, (size_t)p.IK, p_smem);
+    if (!mine) return;
     double P = p.P[e], Ap = p.Ap[e], Bp = p.Bp[e];
     for (int o = 0; o < p.ops.n; ++o) {
-        SG_PCLK(1 + 2 * o)
         const int op = p.ops.get(o);
         if (op == 2) {
-            double tot = 0.0;
-            for (int sh = 0; sh < p.n_shards; ++sh) {
-                const int s0 = (int)((long long)sh * p.n_seg / p.n_shards), s1 = (int)((long long)(sh + 1) * p.n_seg / p.n_shards);
-                // the adds are sequential (specified order); the loads are not: 16 partials are fetched at a time,
-                // the next 16 already in flight while the current ones are added
-                double part = 0.0;
-                const double *src = p.corrE_part + e;
-                double cur[16], nxt[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) cur[u] = (s0 + u < s1) ? src[(size_t)(s0 + u) * p.IK] : 0.0;
-                for (int s = s0; s < s1; s += 16) {
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) nxt[u] = (s + 16 + u < s1) ? src[(size_t)(s + 16 + u) * p.IK] : 0.0;
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) if (s + u < s1) part = part + cur[u];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
-                }
-                tot = tot + part;
-            }
-            SG_PCLK(2 + 2 * o)
             UStream us; us.init(p.key, p.sweep, kStP, (uint32_t)e);
             const double shape = Ap + 1 + (double)p.Zin[e];
-            const double rate = Bp + tot;
+            const double rate = Bp + corrE;
             P = gamma_draw(us, shape, rate);
         } else if (op == 4) {
             Bp = update_b(p.key, p.sweep, kStBp, (uint32_t)e, Ap, P, p.h.ap, p.h.bp);
@@ -549,18 +610,38 @@ __global__ void __launch_bounds__(128) p_family(const PParams p)
             Ap = update_a(p.key, p.sweep, kStAp, (uint32_t)e, Ap, P, Bp, p.h.lp, p.h.var_ap, p.acache, (size_t)e);
         }
     }
-    SG_PCLK(7)
     p.P[e] = P; p.Ap[e] = Ap; p.Bp[e] = Bp;
     if (p.Ps_slot) p.Ps_slot[e] = P;
     if (p.Aps_slot) p.Aps_slot[e] = Ap;
     if (p.Bps_slot) p.Bps_slot[e] = Bp;
 }
+inline size_t p_family_smem_bytes(int n_part) { return blocked_sum_smem_bytes(n_part); }
+
+// column sharding: a shard's ordered sum of its own W E' segment sums, into its slot of the gathered buffer
+__global__ void __launch_bounds__(32 * kPWarps) seg_reduce(const double *part, int n_seg, int IK, double *out_slot)
+{
+    extern __shared__ __align__(16) double p_smem[];
+    const size_t e0 = (size_t)blockIdx.x * kPElems;
+    const double tot = blocked_sum_block(part, n_seg, (size_t)IK, e0, (size_t)IK, p_smem);
+    if (threadIdx.x < kPElems && e0 + threadIdx.x < (size_t)IK) out_slot[e0 + threadIdx.x] = tot;
+}
 
 // ------------------------------------------------------------------------------------------------
 // KE  e_family : gibbs_step3/5/7 (src/gibbs_2.cpp:123-137,156-169,213-251) on K x J,
-//     corrP = P' W (:128) in front, corrE = W E' (:111) segment partials behind.
-// grid = (segments of 128 genomes, groups of 4 classes); thread = (genome, pair of classes).
-// Latency-bound element-wise work: everything is resident in one wave, two elements per thread.
+//     corrP = P' W (:128) in front, corrE = W E' (:111) segment sums behind.
+//
+// The unit of work is a warp task: one column group (32 consecutive genomes = one W E' segment of the draw
+// specification, lane = genome) x one pair of classes, i.e. two elements per lane.  Tasks are numbered column group
+// major and every block takes a CONTIGUOUS range of them (all blocks resident in one wave, the same number of tasks
+// +-1 each), one task per warp per round; a round touches at most two column groups.  The W tile of a column group
+// (up to kERows contexts x 32 genomes, 24 KB) is brought into shared memory ONCE per block by the bulk-copy engine
+// (cp.async.bulk, one 256-byte row each, completion on an mbarrier) and serves both matrix passes:
+//   pass 1  corrP[k,j] = fma chain over the contexts (lanes = genomes read a padded row: conflict-free),
+//   ....    the element updates of this sweep's E-family steps, in permutation order,
+//   pass 2  W E' of the segment for the task's two classes: lanes = contexts, the freshly drawn E values come
+//           from the other lanes' registers by shuffle; the 32-term fma chain in genome order.
+// A task never talks to another warp, so there is no block-wide barrier inside a round.  More than kERows contexts
+// (pentanucleotide cohorts): the tile streams through the two slots in chunks of kERows rows, one column group per round.
 // ------------------------------------------------------------------------------------------------
 struct EParams {
     int I, J, Jp, K;
@@ -579,9 +660,34 @@ struct EParams {
     Ops ops;
 };
 
-constexpr int kEGroup = 4;      // classes per block
+constexpr int kEWarps = 8;
+constexpr int kEThreads = 32 * kEWarps;
+constexpr int kERows = 96;        // contexts per staged chunk of W
+constexpr int kEPitch = 34;       // doubles per staged row: 272 B keeps every row 16-byte aligned for the bulk copies; lanes
+                                  // that walk down a column (pass 2) meet two-way bank conflicts only
+constexpr size_t kESmemBytes = sizeof(double) * 2 * kERows * kEPitch;
 
-__device__ __noinline__ void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
+SG_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SG_D void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+SG_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SG_D void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted in bytes on the mbarrier
+SG_D void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// inlined: the kernel's parameters are read from the constant bank (a call by reference would copy them to the stack,
+// and every p.X inside would be a local-memory load -- 60 % of those missed L1 in the round-1 profile)
+SG_D void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
 {
     double E = p.E[e], Ae = p.Ae[e], Be = p.Be[e];
     const uint32_t eg = (uint32_t)(e + (size_t)p.K * p.col0);        // global element k + K*j of the streams
@@ -607,88 +713,159 @@ __device__ __noinline__ void e_update_element(const EParams &p, size_t e, double
 
 #ifdef SG_Z_TIMING      // experiments only: per-block phase clocks of the last e_family launch
 __device__ long long g_e_clock[4096][5];
-#define SG_ECLK(slot) if (threadIdx.x == 0 && blockIdx.x + gridDim.x * blockIdx.y < 4096) g_e_clock[blockIdx.x + gridDim.x * blockIdx.y][slot] = clock64();
+#define SG_ECLK(slot) if (threadIdx.x == 0 && blockIdx.x < 4096) g_e_clock[blockIdx.x][slot] = clock64();
 #else
 #define SG_ECLK(slot)
 #endif
 
+__host__ __device__ inline int e_pairs(int K) { return (K + 1) / 2; }
+__host__ __device__ inline int e_groups(int J) { return (J + 31) / 32; }
+
 __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
 {
-    SG_ECLK(0)
-    __shared__ __align__(32) double E_s[kSeg * kEGroup];  // [128][4]; classes beyond K and genomes beyond J stay zero
-    const int tid = threadIdx.x, jl = tid & (kSeg - 1), h = tid >> 7;
+    extern __shared__ __align__(128) unsigned char e_smem[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    double *Ws = reinterpret_cast<double *>(e_smem);        // [2][kERows][kEPitch]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int I = p.I, J = p.J, K = p.K;
-    const int seg = blockIdx.x, j0 = seg * kSeg, j = j0 + jl;
-    const int kBegin = blockIdx.y * kEGroup;
-    const int kEnd = min(K, kBegin + kEGroup);
-    const int ka = kBegin + 2 * h, kb = ka + 1;           // this thread's two classes
+    const int npairs = e_pairs(K), n_tasks = e_groups(J) * npairs;
+    const int t_begin = (int)((long long)blockIdx.x * n_tasks / gridDim.x), t_end = (int)((long long)(blockIdx.x + 1) * n_tasks / gridDim.x);
     bool has3 = false;
     for (int o = 0; o < p.ops.n; ++o) has3 |= (p.ops.get(o) == 3);
-    E_s[tid] = 0.0; E_s[tid + kEThreads] = 0.0;           // kSeg * kEGroup == 2 * kEThreads
+    const bool need_w = has3 || p.do_corrE;
+    const int nchunks = (I + kERows - 1) / kERows;
+    const int groups_per_round = nchunks == 1 ? 2 : 1;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    unsigned nload0 = 0, nload1 = 0;                        // tiles sent into each slot so far (uniform over the block)
+    prefetch_tables(tid - 32);
+    SG_ECLK(0)
 
-    if (j < J && ka < kEnd) {
-        // the element state is wanted only after the P'W chain: start bringing it in now
-        {
-            const size_t e = (size_t)ka + (size_t)K * j;
-            sg_prefetch(p.E + e); sg_prefetch(p.Ae + e); sg_prefetch(p.Be + e); sg_prefetch(p.Znj + e);
-            sg_prefetch(p.acache.lg1 + e); sg_prefetch(p.acache.lg2 + e); sg_prefetch(p.acache.lg + e);
+    // warp 0 sends rows [r0, r0 + rows) of column group cg into `slot`
+    auto send_tile = [&](int slot, int cg, int r0) {
+        const int rows = min(kERows, I - r0);
+        if (warp == 0) {
+            uint64_t *bar = &mbar[slot];
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)rows * 256u);
+            __syncwarp();
+            double *dst = Ws + (size_t)slot * kERows * kEPitch;
+            const double *src = p.W + (size_t)r0 * p.Jp + (size_t)cg * 32;
+            for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (size_t)r * kEPitch, src + (size_t)r * p.Jp, 256u, bar);
         }
+        if (slot == 0) ++nload0; else ++nload1;
+    };
+    auto wait_tile = [&](int slot) { mbar_wait(&mbar[slot], ((slot == 0 ? nload0 : nload1) - 1u) & 1u); };
+
+    for (int base = t_begin; base < t_end;) {
+        const int cg0 = base / npairs;
+        const int end = min(t_end, min(base + kEWarps, (cg0 + groups_per_round) * npairs));
+        const int task = base + warp;
+        const bool active = task < end;
+        const int cg = active ? task / npairs : cg0;
+        const int pr = active ? task - cg * npairs : 0;
+        const int ka = 2 * pr, kb = min(ka + 1, K - 1);
+        const bool has_b = ka + 1 < K;
+        const int j = cg * 32 + lane;
+        const bool jin = active && j < J;
+        const size_t ea = (size_t)ka + (size_t)K * min(j, J - 1), eb = (size_t)kb + (size_t)K * min(j, J - 1);
+        if (base != t_begin) __syncthreads();               // every warp is done with the tiles of the previous round
+        if (need_w) {
+            if (nchunks == 1) {
+                send_tile(0, cg0, 0);
+                if ((end - 1) / npairs > cg0) send_tile(1, cg0 + 1, 0);
+            } else {
+                send_tile(0, cg0, 0);
+                send_tile(1, cg0, kERows);
+            }
+        }
+        if (jin && p.ops.n) {                               // the element state is wanted after pass 1: start bringing it in
+            sg_prefetch(p.E + ea); sg_prefetch(p.Ae + ea); sg_prefetch(p.Be + ea); sg_prefetch(p.Znj + ea);
+            sg_prefetch(p.acache.lg1 + ea); sg_prefetch(p.acache.lg2 + ea); sg_prefetch(p.acache.lg + ea);
+        }
+        // ---- pass 1: corrP = P'W for (ka, kb) x this lane's genome
         double acc0 = 0.0, acc1 = 0.0;
         if (has3) {
-            const double *Wc = p.W + j;
-            const double *P0 = p.P + (size_t)I * ka;
-            const double *P1 = p.P + (size_t)I * min(kb, K - 1);
-#pragma unroll 16
-            for (int i = 0; i < I; ++i) {
-                const double w = Wc[(size_t)i * p.Jp];
-                acc0 = fma(__ldg(P0 + i), w, acc0);
-                acc1 = fma(__ldg(P1 + i), w, acc1);
+            for (int c = 0; c < nchunks; ++c) {
+                const int slot = nchunks == 1 ? cg - cg0 : (c & 1);
+                const int r0 = c * kERows, rows = min(kERows, I - r0);
+                if (active) {
+                    wait_tile(slot);
+                    const double *Wt = Ws + (size_t)slot * kERows * kEPitch + lane;
+                    const double *P0 = p.P + (size_t)I * ka + r0, *P1 = p.P + (size_t)I * kb + r0;
+#pragma unroll 8
+                    for (int r = 0; r < rows; ++r) {
+                        const double w = Wt[r * kEPitch];
+                        acc0 = fma(__ldg(P0 + r), w, acc0);
+                        acc1 = fma(__ldg(P1 + r), w, acc1);
+                    }
+                }
+                if (nchunks > 1) {
+                    __syncthreads();                        // the slot is free again
+                    if (c + 2 < nchunks) send_tile(slot, cg0, (c + 2) * kERows);
+                }
             }
         }
         SG_ECLK(1)
-        double Eo;
-        e_update_element(p, (size_t)ka + (size_t)K * j, acc0, Eo);
-        E_s[jl * kEGroup + (ka - kBegin)] = Eo;
-        if (kb < kEnd) {
-            e_update_element(p, (size_t)kb + (size_t)K * j, acc1, Eo);
-            E_s[jl * kEGroup + (kb - kBegin)] = Eo;
-        }
-    }
-    SG_ECLK(2)
-    if (!p.do_corrE) return;
-    __syncthreads();
-    SG_ECLK(3)
-    // W E' of this segment: one thread per context row, the row of W read once (32 genomes in flight) for the block's
-    // four classes -- four independent fma chains, each in ascending genome order
-    const int jn = min(kSeg, J - j0);
-    const int Kn = kEnd - kBegin;
-    const double4 *E4 = reinterpret_cast<const double4 *>(E_s);
-    for (int i = tid; i < I; i += kEThreads) {
-        const double *Wr = p.W + (size_t)i * p.Jp + j0;    // 16-byte aligned: Jp and j0 are multiples of 32
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int c = 0;
-        for (; c + 32 <= jn; c += 32) {
-            double2 w[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) w[u] = *reinterpret_cast<const double2 *>(Wr + c + 2 * u);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const double4 e0 = E4[c + 2 * u], e1 = E4[c + 2 * u + 1];
-                a0 = fma(w[u].x, e0.x, a0); a1 = fma(w[u].x, e0.y, a1); a2 = fma(w[u].x, e0.z, a2); a3 = fma(w[u].x, e0.w, a3);
-                a0 = fma(w[u].y, e1.x, a0); a1 = fma(w[u].y, e1.y, a1); a2 = fma(w[u].y, e1.z, a2); a3 = fma(w[u].y, e1.w, a3);
+        // ---- the element updates of this sweep, two elements per lane
+        double Ea = 0.0, Eb = 0.0;
+        if (jin) {
+            if (p.ops.n) {
+#pragma unroll 1
+                for (int el = 0; el < (has_b ? 2 : 1); ++el) {          // one copy of the inlined update code
+                    double Eo;
+                    e_update_element(p, el ? eb : ea, el ? acc1 : acc0, Eo);
+                    if (el) Eb = Eo; else Ea = Eo;
+                }
+            } else {
+                Ea = p.E[ea];
+                if (has_b) Eb = p.E[eb];
             }
         }
-        for (; c < jn; ++c) {
-            const double wv = Wr[c];
-            const double4 e0 = E4[c];
-            a0 = fma(wv, e0.x, a0); a1 = fma(wv, e0.y, a1); a2 = fma(wv, e0.z, a2); a3 = fma(wv, e0.w, a3);
+        SG_ECLK(2)
+        if (!p.do_corrE) { base = end; continue; }
+        // ---- pass 2: W E' of this segment for (ka, kb): lanes = contexts, E by shuffle, fma chain in genome order
+        if (nchunks > 1 && has3) {                          // restart the stream of chunks
+            send_tile(0, cg0, 0);
+            send_tile(1, cg0, kERows);
         }
-        double *dst = p.corrE_part + (size_t)seg * ((size_t)I * K) + (size_t)i + (size_t)I * kBegin;
-        dst[0] = a0;
-        if (Kn > 1) dst[(size_t)I] = a1;
-        if (Kn > 2) dst[(size_t)I * 2] = a2;
-        if (Kn > 3) dst[(size_t)I * 3] = a3;
+        for (int c = 0; c < nchunks; ++c) {
+            const int slot = nchunks == 1 ? cg - cg0 : (c & 1);
+            const int r0 = c * kERows, rows = min(kERows, I - r0);
+            if (active) {
+                wait_tile(slot);
+                const double *Wt = Ws + (size_t)slot * kERows * kEPitch;
+                const int ra = lane, rb = lane + 32, rc = lane + 64;      // kERows == 96: three rows per lane
+                const double *W0 = Wt + (size_t)min(ra, rows - 1) * kEPitch, *W1 = Wt + (size_t)min(rb, rows - 1) * kEPitch,
+                             *W2 = Wt + (size_t)min(rc, rows - 1) * kEPitch;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll 4
+                for (int jj = 0; jj < 32; ++jj) {
+                    const double xa = __shfl_sync(kFull, Ea, jj), xb = __shfl_sync(kFull, Eb, jj);
+                    const double w0 = W0[jj], w1 = W1[jj], w2 = W2[jj];
+                    a0 = fma(w0, xa, a0); a1 = fma(w1, xa, a1); a2 = fma(w2, xa, a2);
+                    b0 = fma(w0, xb, b0); b1 = fma(w1, xb, b1); b2 = fma(w2, xb, b2);
+                }
+                double *da = p.corrE_part + (size_t)cg * ((size_t)I * K) + (size_t)I * ka + r0;
+                double *db = p.corrE_part + (size_t)cg * ((size_t)I * K) + (size_t)I * kb + r0;
+                if (ra < rows) da[ra] = a0;
+                if (rb < rows) da[rb] = a1;
+                if (rc < rows) da[rc] = a2;
+                if (has_b) {
+                    if (ra < rows) db[ra] = b0;
+                    if (rb < rows) db[rb] = b1;
+                    if (rc < rows) db[rc] = b2;
+                }
+            }
+            if (nchunks > 1) {
+                __syncthreads();
+                if (c + 2 < nchunks) send_tile(slot, cg0, (c + 2) * kERows);
+            }
+        }
+        SG_ECLK(3)
+        base = end;
     }
     SG_ECLK(4)
 }
@@ -988,17 +1165,6 @@ __global__ void median_rows(const double *T, int n, int R, double *out)
 }
 
 // ------------------------------------------------------------------------------------------------
-// column sharding: a shard adds its own W E' segment partials in order into its slot of the gathered
-// buffer (the other slots stay zero, so the all-reduce over shards is exact in any order)
-// ------------------------------------------------------------------------------------------------
-__global__ void seg_reduce(const double *part, int n_seg, int IK, double *out_slot)
-{
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= IK) return;
-    double acc = 0.0;
-    for (int s = 0; s < n_seg; ++s) acc = acc + part[(size_t)s * IK + e];
-    out_slot[e] = acc;
-}
 // same-device emulation of the all-reduce (shards sharing one GPU, for tests): every buffer <- sum of all
 template <typename T>
 __global__ void sum_shards(T *const *bufs, int n_shards, size_t n)

@@ -61,6 +61,12 @@ int ensure_device_setup(int device)
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
     CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (33 K + 3264) bytes: above 48 KB from K = 88 (K <= 128 is accepted)
     CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, e_family));             // two W tiles: 51 KB
+    CU(cudaFuncSetAttribute(e_family, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, p_family));             // scratch of the ordered W E' sums grows with the number of genomes
+    CU(cudaFuncSetAttribute(p_family, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, seg_reduce));
+    CU(cudaFuncSetAttribute(seg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
 #ifdef SG_Z_CARVEOUT
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, SG_Z_CARVEOUT));
 #endif
@@ -95,6 +101,16 @@ int upload_data(int device, int I, int J, const double *M, const double *W, std:
     static_assert(kNDirect == 32, "cohort.cu sorts the work list with the same threshold (kListDirect)");
     ST(sgh::get_cohort(device, I, J, M, W, col0, Jglobal, out));
     return ensure_lgm(*out);
+}
+
+// SIGNER_SYNC_LAUNCHES=1 (debugging): wait for every kernel right after its launch and name the one that failed
+const bool g_sync_launches = [] { const char *e = std::getenv("SIGNER_SYNC_LAUNCHES"); return e && e[0] == '1'; }();
+int check_launch(cudaStream_t st, const char *kernel)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && g_sync_launches) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(SIGNER_ERR_CUDA, std::string(kernel) + ": " + cudaGetErrorString(e));
+    return SIGNER_OK;
 }
 
 struct Ring {
@@ -132,7 +148,7 @@ struct signer_chain {
     unsigned *ll_ticket = nullptr;               // block counter of loglik_cols' fused tree
     unsigned long long z_launches = 0;
     int z_grid = 0, z_warps = 8, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
-    int ksplit = 1;
+    int e_grid = 1, sms = 1;
     Hyper h{};
     Key key{};
     uint32_t sweep0 = 0;
@@ -242,7 +258,7 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
         ProfScope ps(c, 0);
         z_alloc_fused<<<c->z_grid, 32 * c->z_warps, (size_t)c->z_warp_smem * c->z_warps + (c->z_zin_smem ? c->nP * sizeof(int) : 0), c->stream>>>(p);
     }
-    CU(cudaGetLastError());
+    ST(check_launch(c->stream, "z_alloc_fused"));
     c->z_launches++;
     c->launches++;
     c->zcur = tgt;
@@ -254,18 +270,18 @@ int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double
     PParams p{};
     p.IK = (int)c->nP; p.P = c->P; p.Ap = c->Ap; p.Bp = c->Bp;
     p.Zin = c->Zin[c->zcur];
-    if (c->n_shards > 1) { p.corrE_part = c->corrE_all; p.n_seg = c->n_shards; p.n_shards = c->n_shards; }
-    else { p.corrE_part = c->corrE_part; p.n_seg = c->n_seg; p.n_shards = 1; }
+    if (c->n_shards > 1) { p.corrE_part = c->corrE_all; p.n_part = c->n_shards; }      // the shards' ordered sums
+    else { p.corrE_part = c->corrE_part; p.n_part = c->n_seg; }                          // the segment sums
     p.Ps_slot = Ps; p.Aps_slot = Aps; p.Bps_slot = Bps;
     p.acache = ACache{c->acache_p, c->acache_p + c->nP, c->acache_p + 2 * c->nP};
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 1);
-        p_family<<<(p.IK + 127) / 128, 128, 0, c->stream>>>(p);
+        p_family<<<(p.IK + kPElems - 1) / kPElems, 32 * kPWarps, p_family_smem_bytes(p.n_part), c->stream>>>(p);
     }
     c->launches++;
-    CU(cudaGetLastError());
+    ST(check_launch(c->stream, "p_family"));
     return SIGNER_OK;
 }
 
@@ -283,10 +299,10 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 2);
-        e_family<<<dim3(c->n_seg, c->ksplit), kEThreads, 0, c->stream>>>(p);
+        e_family<<<c->e_grid, kEThreads, kESmemBytes, c->stream>>>(p);
     }
     c->launches++;
-    CU(cudaGetLastError());
+    ST(check_launch(c->stream, "e_family"));
     return SIGNER_OK;
 }
 
@@ -297,7 +313,7 @@ int launch_loglik_cols(signer_chain *c, double *out = nullptr, cudaStream_t st =
                 out ? c->col : nullptr, c->data->n2, c->data->lgm, out, c->ll_ticket};
     loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(c->K), st ? st : c->stream>>>(lp);
     c->launches++;
-    CU(cudaGetLastError());
+    ST(check_launch(st ? st : c->stream, "loglik_cols"));
     return SIGNER_OK;
 }
 
@@ -607,7 +623,11 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     }
     c->z_warps = best_w;
     c->z_grid = std::max(1, std::min((c->n_chunks + best_w - 1) / best_w, best_b * sms));
-    c->ksplit = (K + kEGroup - 1) / kEGroup;
+    // e_family: every block takes a contiguous range of warp tasks (column group x class pair); all blocks resident in one wave
+    c->sms = sms;
+    c->e_grid = std::max(1, std::min(3 * sms, (e_groups(c->J) * e_pairs(K) + kEWarps - 1) / kEWarps));
+    if (p_family_smem_bytes(c->n_seg) > (size_t)g_z_dyn_smem_max[c->device])
+        return fail(SIGNER_ERR_ARG, "too many genomes for one device: the W E' sums do not fit the reduction's shared memory; shard the columns");
 
     // initial sufficient statistics: reduce the given cube, or draw the first allocation on the device
     if (deferred_init) {                                  // a column shard: its peers take part (sharded_run)
@@ -714,7 +734,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
                 if (do_stats) {
                     stats_reduce<<<256, 256, 0, c->stream>>>(rg.Aps, rg.Bps, c->nP * (size_t)(slot + 1), c->stats);
                     stats_reduce<<<1024, 256, 0, c->stream>>>(rg.Aes, rg.Bes, c->nE * (size_t)(slot + 1), c->stats + 4);
-                    CU(cudaGetLastError());
+                    ST(check_launch(c->stream, "stats_reduce"));
                     c->launches += 2;
                 }
                 CU(cudaEventRecord(rg.filled, c->stream));
@@ -855,7 +875,8 @@ int shard_launch_e(ShardSet &S, uint32_t sweep, const Ops &ops, int do_corrE, co
         ST(launch_e(c, sweep, ops, do_corrE, sl ? sl->Es : nullptr, sl ? sl->Aes : nullptr, sl ? sl->Bes : nullptr));
         if (do_corrE) {
             CU(cudaMemsetAsync(c->corrE_all, 0, sizeof(double) * c->nP * S.n, c->stream));
-            seg_reduce<<<((int)c->nP + 127) / 128, 128, 0, c->stream>>>(c->corrE_part, c->n_seg, (int)c->nP, c->corrE_all + c->nP * g);
+            seg_reduce<<<(unsigned)((c->nP + kPElems - 1) / kPElems), 32 * kPWarps, blocked_sum_smem_bytes(c->n_seg), c->stream>>>(
+                c->corrE_part, c->n_seg, (int)c->nP, c->corrE_all + c->nP * g);
             CU(cudaGetLastError());
         }
         all[g] = c->corrE_all;
@@ -904,7 +925,7 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
     const int I = pr->I, J = pr->J, K = pr->K;
     if (n_dev < 1 || n_dev > 64) return fail(SIGNER_ERR_ARG, "sharded run: 1..64 shards");
     const int n_seg = (J + kSeg - 1) / kSeg;
-    if (n_dev > n_seg) return fail(SIGNER_ERR_ARG, "sharded run: more shards than 128-genome segments");
+    if (n_dev > n_seg) return fail(SIGNER_ERR_ARG, "sharded run: more shards than 32-genome segments");
     ShardSet S;
     S.n = n_dev;
     for (int g = 1; g < n_dev; ++g) if (devices[g] != devices[0]) S.same_device = false;
@@ -1398,10 +1419,6 @@ void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 extern "C" int signer_debug_e_clocks(long long *out, int nblocks)
 {
     return (int)cudaMemcpyFromSymbol(out, sg::g_e_clock, sizeof(long long) * 5 * (size_t)nblocks);
-}
-extern "C" int signer_debug_p_clocks(long long *out, int nblocks)
-{
-    return (int)cudaMemcpyFromSymbol(out, sg::g_p_clock, sizeof(long long) * 8 * (size_t)nblocks);
 }
 extern "C" int signer_debug_z_phases(unsigned long long *out)
 {

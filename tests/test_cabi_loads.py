@@ -25,7 +25,7 @@ def test_header_symbols_exported(sg):
 
 def test_version_and_no_gpu_error_text(sg):
     L = _lib.lib()
-    assert L.signer_version() == 3 and L.signer_draw_spec_version() == 6
+    assert L.signer_version() == 3 and L.signer_draw_spec_version() == 7
     n = L.signer_device_count()
     if n < 0:       # CPU container: a status, not a crash
         assert n == -3 and L.signer_last_error()

@@ -1,4 +1,4 @@
-"""Golden vectors of the draw specification (tests/golden/spec_v6.npz, made by make_golden.py):
+"""Golden vectors of the draw specification (tests/golden/spec_v7.npz, made by make_golden.py):
 the oracle must reproduce them here on the CPU, the CUDA path on the GPU."""
 import ctypes as C
 import os
@@ -8,7 +8,7 @@ import pytest
 
 from helpers import assert_bits_equal
 
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spec_v6.npz"))
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spec_v7.npz"))
 STATE = ("P", "E", "Ap", "Bp", "Ae", "Be")
 
 
@@ -27,6 +27,26 @@ def test_oracle_reproduces_golden_chain(oracle):
     r = oracle.gibbs_run(G["chain_M"], G["chain_W"], None, *[st[k] for k in STATE], burn=6, eval=3, seed=4242)
     for k in ("Ps", "Es", "Aps", "Bps", "Aes", "Bes", "Z", "loglik", "Zin", "Znj"):
         assert_bits_equal(r[k], G["chain_" + k], k)
+
+
+def test_oracle_reproduces_golden_wide_chain(oracle):
+    """35 W E' segments: two levels of the blocked ordered sum (draw specification v7)"""
+    st = {k: G["wide_init_" + k] for k in STATE}
+    r = oracle.gibbs_run(G["wide_M"], G["wide_W"], None, *[st[k] for k in STATE], burn=2, eval=2, seed=4243)
+    for k in ("Ps", "Es", "Bps", "Bes", "loglik", "Zin", "Znj"):
+        assert_bits_equal(r[k], G["wide_" + k], k)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_wide_chain(sg):
+    from signer_b200 import synth
+    st = {k: G["wide_init_" + k] for k in STATE}
+    got = sg.GibbsSamplerCpp(G["wide_M"], G["wide_W"], None, *[st[k] for k in STATE], *synth.hyper_tuple(), 2, 2,
+                             False, False, False, False, True, seed=4243)
+    assert_bits_equal(got[2], G["wide_Ps"], "Ps"); assert_bits_equal(got[3], G["wide_Es"], "Es")
+    assert_bits_equal(got[5], G["wide_Bps"], "Bps"); assert_bits_equal(got[7], G["wide_Bes"], "Bes")
+    assert_bits_equal(got.loglik, G["wide_loglik"], "loglik")
+    assert np.array_equal(got.Zin, G["wide_Zin"].astype(np.int64)) and np.array_equal(got.Znj, G["wide_Znj"].astype(np.int64))
 
 
 @pytest.mark.gpu
