@@ -4,7 +4,7 @@
 # turns them into the text summaries committed under profiles/.
 set -x
 TAG=${1:-r01}
-CMD="python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e --no-extras"
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1

@@ -37,7 +37,7 @@ if os.path.exists(lf):
         tot[name][0] += 1; tot[name][1] += v
     s = sum(v[1] for v in tot.values())
     with open(os.path.join(P, "%s_launch_list.txt" % tag), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 : python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 : python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e --no-extras\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("%-40s %8s %14s %12s %8s\n" % ("kernel", "launches", "total_ns", "mean_us", "share"))
         for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):

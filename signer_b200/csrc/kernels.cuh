@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
 
         SG_ZCLK(2)                                          // direct loop
         // ---- large counts
+        bool claimed_late = false;
         if (__any_sync(kFull, nrem > 0)) {
             // visiting order: counting sort of the classes by d = min(7, expo(S) - expo(P*E)), ties by index
             if (nrem > 0) {
@@ -386,6 +387,12 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                 z_emit(p, zin_s, row, col, ord[(K - 1) * 32], nrem);
                 nrem = 0;
             }
+            // the chains are done; what is left of this batch is short (at most kNTail draws per cell): claim the
+            // successor now so that the round trip of the claim hides behind the remainder draws
+#ifndef SG_NO_LATE_CLAIM
+            if (!early && lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+            claimed_late = !early;
+#endif
             // the remainder goes to the unvisited classes by the direct method: the lane's column becomes the
             // cumulative sums in index order with the visited classes zeroed; draw d of a cell uses word d&3 of
             // block kTailBlock0 + (d>>2) of the cell's stream and the same search as the small counts.  The warp
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
         if (lane == 0 && t_batch < (1 << 16)) g_z_batch_cycles[t_batch] = (unsigned)(clock64() - t_begin);
 #endif
         if (!early) {
-            if (lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+            if (lane == 0 && !claimed_late) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
             nxt = __shfl_sync(kFull, pend, 0);
             const int cell = nxt * 32 + lane;
             if (nxt < p.n_batches && cell < p.n_cells) { n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell]; }
@@ -514,7 +521,7 @@ struct Ops {
 // Call with all threads of the block; threads 0..31 get their element's total.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSumBlk = 32;
-constexpr int kPWarps = 8, kPElems = 32;
+constexpr int kPWarps = 16, kPElems = 32;   // p_family: 16 warps per block of 32 elements
 __host__ __device__ inline int sum_blocks(int n) { return (n + kSumBlk - 1) / kSumBlk; }
 __host__ __device__ inline int blocked_sum_pitch(int n) { return sum_blocks(n) | 1; }
 __host__ __device__ inline size_t blocked_sum_smem_bytes(int n) { return sizeof(double) * kPElems * (size_t)blocked_sum_pitch(n); }
@@ -582,20 +589,30 @@ struct PParams {
 __global__ void __launch_bounds__(32 * kPWarps) p_family(const PParams p)
 {
     extern __shared__ __align__(16) double p_smem[];
-    const int tid = threadIdx.x;
+    __shared__ double tot_s[kPElems];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int e0 = blockIdx.x * kPElems;
     bool has2 = false;
     for (int o = 0; o < p.ops.n; ++o) has2 |= (p.ops.get(o) == 2);
-    double corrE = 0.0;
-    prefetch_tables(tid - 32);                              // warps 1 and 2, while warp 0 starts on its state
-    const int e = e0 + tid;
-    const bool mine = tid < kPElems && e < p.IK;
+    // The element updates are one long dependent chain per element, and a warp pays for every rare path (a rejected
+    // proposal, a ziggurat wedge, the logarithmic acceptance test) that ANY of its lanes takes.  With 32 elements in one
+    // warp that is all of them, every time; two elements per warp keeps the chain near its expected length, and the
+    // 16 warps of the block interleave on the four schedulers.
+    constexpr int kPerWarp = kPElems / kPWarps;
+    const int e = e0 + warp * kPerWarp + lane;
+    const bool mine = lane < kPerWarp && e < p.IK;
+    if (lane >= kPerWarp) prefetch_tables((warp & 1) * 30 + lane - kPerWarp);   // even warps: lines 0..29, odd warps: the rest
     if (mine) {                                             // what the element updates will want, on its way before the sums
         sg_prefetch(p.P + e); sg_prefetch(p.Ap + e); sg_prefetch(p.Bp + e); sg_prefetch(p.Zin + e);
         sg_prefetch(p.acache.lg1 + e); sg_prefetch(p.acache.lg2 + e); sg_prefetch(p.acache.lg + e);
     }
-    if (has2) corrE = blocked_sum_block(p.corrE_part, p.n_part, (size_t)p.IK, (size_t)e0, (size_t)p.IK, p_smem);
+    if (has2) {
+        const double t = blocked_sum_block(p.corrE_part, p.n_part, (size_t)p.IK, (size_t)e0, (size_t)p.IK, p_smem);
+        if (tid < kPElems) tot_s[tid] = t;
+        __syncthreads();
+    }
     if (!mine) return;
+    const double corrE = has2 ? tot_s[warp * kPerWarp + lane] : 0.0;
     double P = p.P[e], Ap = p.Ap[e], Bp = p.Bp[e];
     for (int o = 0; o < p.ops.n; ++o) {
         const int op = p.ops.get(o);

@@ -121,8 +121,11 @@ struct Ring {
 
 } // namespace
 
+struct ShardLink;     // column sharding: this chain is one shard of a chain over several GPUs (see sharded_run)
+
 struct signer_chain {
     std::shared_ptr<DeviceData> data;
+    ShardLink *link = nullptr;
     int device = 0, I = 0, J = 0, Jp = 0, K = 0;
     size_t nP = 0, nE = 0, nPp = 0, nEp = 0;   // matrix sizes, and padded to 32 doubles inside the state block
     // one allocation [P | Ap | Bp | E | Ae | Be]: the state goes up and comes back with ONE copy through a pinned buffer
@@ -215,6 +218,12 @@ struct ProfScope {
     }
 };
 
+// the exchange steps of a column-sharded chain (defined with sharded_run)
+template <typename T> int shard_sum(signer_chain *c, T *buf, size_t count);
+int shard_gather_corrE(signer_chain *c);
+int shard_loglik(signer_chain *c, int mode_lgm, double *out0);
+bool is_sharded(const signer_chain *c);
+
 // a kernel that writes P or E is about to be enqueued: the pending log-likelihood must have read them
 int wait_loglik(signer_chain *c)
 {
@@ -262,6 +271,7 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     c->z_launches++;
     c->launches++;
     c->zcur = tgt;
+    if (is_sharded(c)) ST(shard_sum<int>(c, c->Zin[tgt], c->nP));       // exchange 1: the context statistics of all shards
     return SIGNER_OK;
 }
 
@@ -303,6 +313,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     }
     c->launches++;
     ST(check_launch(c->stream, "e_family"));
+    if (do_corrE && is_sharded(c)) ST(shard_gather_corrE(c));           // exchange 2: every shard's ordered W E' sum
     return SIGNER_OK;
 }
 
@@ -320,6 +331,7 @@ int launch_loglik_cols(signer_chain *c, double *out = nullptr, cudaStream_t st =
 // log-likelihood of the current state into out[0], on the side stream (see signer_chain::ll_stream)
 int launch_loglik(signer_chain *c, double *out)
 {
+    if (is_sharded(c)) return shard_loglik(c, 0, out);     // on the launching stream: the shards meet in an all-reduce
     ST(wait_loglik(c));                                    // one in flight at a time: they share col and the ticket
     CU(cudaEventRecord(c->ll_ready, c->stream));
     CU(cudaStreamWaitEvent(c->ll_stream, c->ll_ready, 0));
@@ -446,9 +458,18 @@ int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signe
         if (!dst || !src) return;
         pool.post_d2h(src, dst + per * (size_t)r0, sizeof(double) * per * (size_t)cnt, r.filled, r.inflight);
     };
-    if (!c->sumPs) { cp(out->Ps, r.Ps, c->nP); cp(out->Es, r.Es, c->nE); }   // else: from the full-length stores at the end
-    cp(out->Bps, r.Bps, c->nP); cp(out->Bes, r.Bes, c->nE);
-    if (keep_par) { cp(out->Aps, r.Aps, c->nP); cp(out->Aes, r.Aes, c->nE); }
+    // a column shard: its genomes are a contiguous block of every K x J slice of the caller's cube
+    auto cp_shard = [&](double *dst, const double *src) {
+        if (!dst || !src) return;
+        const size_t slice = (size_t)c->K * c->data->Jglobal, off = (size_t)c->K * c->col0;
+        for (int s = 0; s < cnt; ++s)
+            pool.post_d2h(src + c->nE * (size_t)s, dst + slice * (size_t)(r0 + s) + off, sizeof(double) * c->nE, r.filled, r.inflight);
+    };
+    const bool shard = is_sharded(c);
+    if (!c->sumPs) { cp(out->Ps, r.Ps, c->nP); if (shard) cp_shard(out->Es, r.Es); else cp(out->Es, r.Es, c->nE); }   // else: from the full-length stores at the end
+    cp(out->Bps, r.Bps, c->nP);
+    if (shard) cp_shard(out->Bes, r.Bes); else cp(out->Bes, r.Bes, c->nE);
+    if (keep_par) { cp(out->Aps, r.Aps, c->nP); if (shard) cp_shard(out->Aes, r.Aes); else cp(out->Aes, r.Aes, c->nE); }
     return SIGNER_OK;
 }
 
@@ -684,10 +705,11 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     int chunk_r0 = 0;
     std::vector<std::thread> faulters;
     auto join_faulters = [&]() { for (auto &t : faulters) if (t.joinable()) t.join(); faulters.clear(); };
-    if (out && eval > 0) {
+    if (out && eval > 0 && (!is_sharded(c) || c->shard == 0)) {      // (the first shard touches the caller's pages for all)
         const size_t R = (size_t)eval;
         double *bufs[7] = {out->Es, out->Bes, keep_par ? out->Aes : nullptr, out->Ps, out->Bps, keep_par ? out->Aps : nullptr, zcube ? out->Zs : nullptr};
-        const size_t lens[7] = {c->nE * R, c->nE * R, c->nE * R, c->nP * R, c->nP * R, c->nP * R, (size_t)c->I * c->J * c->K};
+        const size_t nEg = (size_t)c->K * c->data->Jglobal;                  // the caller's arrays hold the whole cohort
+        const size_t lens[7] = {nEg * R, nEg * R, nEg * R, c->nP * R, c->nP * R, c->nP * R, (size_t)c->I * c->data->Jglobal * c->K};
         // large arrays are touched by several threads each (page faults scale across threads); the touch is an atomic
         // no-op, so it can never undo a copy-out that has already landed (host_util.cu)
         const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
@@ -752,7 +774,12 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined.  The cube leaves
             // through the transfer pool like the samples (pageable destination).
             CU(cudaEventRecord(c->cube_done, c->stream));
-            TransferPool::of(c->device).post_d2h(zcube, out->Zs, sizeof(double) * (size_t)c->I * c->J * c->K, c->cube_done, cube_group);
+            TransferPool &pool = TransferPool::of(c->device);
+            if (!is_sharded(c)) pool.post_d2h(zcube, out->Zs, sizeof(double) * (size_t)c->I * c->J * c->K, c->cube_done, cube_group);
+            else                                           // a shard's block of every I x J slice
+                for (int k = 0; k < c->K; ++k)
+                    pool.post_d2h(zcube + (size_t)c->I * c->J * k, out->Zs + (size_t)c->I * c->data->Jglobal * k + (size_t)c->I * c->col0,
+                                  sizeof(double) * (size_t)c->I * c->J, c->cube_done, cube_group);
         }
         CU(cudaStreamSynchronize(c->stream));
         if (want_rings) { ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1])); }
@@ -779,15 +806,21 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
 }
 
 // ------------------------------------------------------------------------------------------------
-// Genome-column sharding: one chain over several GPUs.  Shard g owns the 128-genome
+// Genome-column sharding: one chain over several GPUs.  Shard g owns the 32-genome
 // segments [g*n_seg/N, (g+1)*n_seg/N) -- M, W, E, Ae, Be, Znj for those genomes; P, Ap, Bp are
 // replicated and updated redundantly with identical Philox counters, so they stay identical.
-// Per sweep two exchanges of I*K values: the integer sums Zin after step 1 and the shards' ordered
-// W E' sums after step 3 (every shard fills only its slot of an [N][I*K] buffer, so the all-reduce
-// adds zeros and is exact in any order); per evaluation sweep one all-reduce of the per-genome
-// log-likelihood terms.  Results are bit-identical to the oracle run with nshards = N.
-// NCCL (all-reduce over NVLink) is loaded lazily; shards placed on ONE device are emulated with a
-// summing kernel so that the logic is testable on a single GPU.
+// Every shard is an ordinary chain with a ShardLink and runs the ordinary sweep loop (chain_run) on its
+// OWN host thread, so the devices are fed in parallel; the path's real exchange steps hang off the
+// kernels that produce their inputs (launch_z, launch_e, launch_loglik):
+//   * after step 1: ncclAllReduce (sum, int32) of the I*K context statistics Zin -- exact in any order;
+//   * after step 3: every shard adds its own W E' segment sums in the specified order (seg_reduce) and
+//     one ncclAllGather hands every shard all N ordered sums (I*K doubles each), which p_family then adds
+//     in shard order;
+//   * per evaluation sweep: an all-reduce of the per-genome log-likelihood terms (disjoint supports),
+//     then the tree on shard 0.
+// Results are bit-identical to the oracle run with nshards = N.  NCCL is loaded lazily; shards placed on
+// ONE device (tests on a single GPU) share one stream and emulate the collectives with a summing kernel
+// between two host-side barriers.
 // ------------------------------------------------------------------------------------------------
 typedef void *nccl_comm_t;
 struct NcclApi {
@@ -795,8 +828,7 @@ struct NcclApi {
     int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
-    int (*GroupStart)() = nullptr;
-    int (*GroupEnd)() = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load()
     {
@@ -807,285 +839,216 @@ struct NcclApi {
         CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
-        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
-        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-        return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+        return CommInitAll && CommDestroy && AllReduce && AllGather;
     }
 };
 constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0;   // nccl.h: ncclInt32, ncclFloat64, ncclSum
 
-struct ShardSet {
-    int n = 0;
-    bool same_device = true;
-    std::vector<signer_chain *> sh;
-    std::vector<nccl_comm_t> comms;
-    NcclApi nccl;
-    void **ptr_tab = nullptr;        // device table of buffer pointers for the same-device emulation
-    ~ShardSet()
+// the shards' host threads meet here (emulated collectives only); wait() returns false once any of them has failed
+struct HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 1, waiting = 0;
+    unsigned long gen = 0;
+    bool aborted = false;
+    bool wait()
     {
-        for (auto it = sh.rbegin(); it != sh.rend(); ++it) delete *it;     // shard 0 last: emulated shards launch on its stream
+        std::unique_lock<std::mutex> lk(mu);
+        if (aborted) return false;
+        const unsigned long g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return true; }
+        cv.wait(lk, [&] { return gen != g || aborted; });
+        return !aborted;
+    }
+    void abort()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        aborted = true;
+        cv.notify_all();
+    }
+};
+
+struct ShardShared {
+    int n = 0;
+    bool emulated = true;
+    NcclApi nccl;
+    std::vector<nccl_comm_t> comms;
+    HostBarrier bar;
+    std::vector<void *> bufs;        // emulated collectives: this round's buffer of every shard
+    void **ptr_tab = nullptr;        // ... and their device table
+    ~ShardShared()
+    {
         for (auto cm : comms) if (cm && nccl.CommDestroy) nccl.CommDestroy(cm);
         if (ptr_tab) cudaFree(ptr_tab);
     }
 };
 
-// all-reduce (sum) of one buffer per shard, in place
-template <typename T>
-int shard_allreduce(ShardSet &S, const std::vector<T *> &bufs, size_t count)
+} // namespace
+
+struct ShardLink {
+    int rank = 0, n = 1;
+    ShardShared *sh = nullptr;
+};
+
+namespace {
+
+bool is_sharded(const signer_chain *c) { return c->link && c->link->n > 1; }
+
+int nccl_fail(ShardShared *S, const char *what, int rc)
 {
-    if (S.n == 1) return SIGNER_OK;
-    if (S.same_device) {
-        signer_chain *c0 = S.sh[0];
-        CU(cudaSetDevice(c0->device));
-        CU(cudaMemcpyAsync(S.ptr_tab, bufs.data(), sizeof(void *) * S.n, cudaMemcpyHostToDevice, c0->stream));
-        sum_shards<T><<<(unsigned)std::min<size_t>((count + 255) / 256, 1024), 256, 0, c0->stream>>>(reinterpret_cast<T *const *>(S.ptr_tab), S.n, count);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c0->stream));    // the host-side pointer table is reused by the next call
+    return fail(SIGNER_ERR_NCCL, std::string(what) + ": " + (S->nccl.GetErrorString ? S->nccl.GetErrorString(rc) : "error"));
+}
+
+// every shard's buf <- sum over the shards, in place (the producers are already enqueued on the shards' streams)
+template <typename T>
+int shard_sum(signer_chain *c, T *buf, size_t count)
+{
+    ShardLink *L = c->link;
+    if (!L || L->n == 1) return SIGNER_OK;
+    ShardShared *S = L->sh;
+    if (!S->emulated) {
+        const int rc = S->nccl.AllReduce(buf, buf, count, sizeof(T) == 4 ? kNcclInt32 : kNcclFloat64, kNcclSum, S->comms[L->rank], c->stream);
+        if (rc) return nccl_fail(S, "ncclAllReduce", rc);
         return SIGNER_OK;
     }
-    const int dt = sizeof(T) == 4 ? kNcclInt32 : kNcclFloat64;
-    int rc = S.nccl.GroupStart();
-    for (int g = 0; g < S.n && rc == 0; ++g)
-        rc = S.nccl.AllReduce(bufs[g], bufs[g], count, dt, kNcclSum, S.comms[g], S.sh[g]->stream);
-    const int rc2 = S.nccl.GroupEnd();
-    if (rc || rc2) return fail(SIGNER_ERR_NCCL, std::string("ncclAllReduce: ") + (S.nccl.GetErrorString ? S.nccl.GetErrorString(rc ? rc : rc2) : "error"));
-    return SIGNER_OK;
-}
-
-int shard_launch_z(ShardSet &S, uint32_t sweep, uint32_t stream_id, bool cube)
-{
-    std::vector<int *> zin(S.n);
-    for (int g = 0; g < S.n; ++g) {
-        signer_chain *c = S.sh[g];
-        CU(cudaSetDevice(c->device));
-        ST(launch_z(c, sweep, stream_id, cube ? c->Zcube : nullptr));
-        zin[g] = c->Zin[c->zcur];
-    }
-    return shard_allreduce<int>(S, zin, S.sh[0]->nP);
-}
-
-int shard_launch_e(ShardSet &S, uint32_t sweep, const Ops &ops, int do_corrE, const std::vector<Slots> *slots)
-{
-    std::vector<double *> all(S.n);
-    for (int g = 0; g < S.n; ++g) {
-        signer_chain *c = S.sh[g];
-        CU(cudaSetDevice(c->device));
-        const Slots *sl = slots ? &(*slots)[g] : nullptr;
-        ST(launch_e(c, sweep, ops, do_corrE, sl ? sl->Es : nullptr, sl ? sl->Aes : nullptr, sl ? sl->Bes : nullptr));
-        if (do_corrE) {
-            CU(cudaMemsetAsync(c->corrE_all, 0, sizeof(double) * c->nP * S.n, c->stream));
-            seg_reduce<<<(unsigned)((c->nP + kPElems - 1) / kPElems), 32 * kPWarps, blocked_sum_smem_bytes(c->n_seg), c->stream>>>(
-                c->corrE_part, c->n_seg, (int)c->nP, c->corrE_all + c->nP * g);
-            CU(cudaGetLastError());
+    S->bufs[L->rank] = buf;
+    if (!S->bar.wait()) return fail(SIGNER_ERR_CUDA, "a peer shard failed");
+    int rc = SIGNER_OK;
+    if (L->rank == 0) {                                   // one stream carries all emulated shards: plain ordering
+        cudaError_t e = cudaMemcpyAsync(S->ptr_tab, S->bufs.data(), sizeof(void *) * S->n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            sum_shards<T><<<(unsigned)std::min<size_t>((count + 255) / 256, 1024), 256, 0, c->stream>>>(reinterpret_cast<T *const *>(S->ptr_tab), S->n, count);
+            e = cudaGetLastError();
         }
-        all[g] = c->corrE_all;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);    // the host-side pointer table is reused by the next round
+        if (e != cudaSuccess) { rc = fail(SIGNER_ERR_CUDA, std::string("emulated all-reduce: ") + cudaGetErrorString(e)); S->bar.abort(); }
     }
-    if (do_corrE) return shard_allreduce<double>(S, all, S.sh[0]->nP * S.n);
+    if (!S->bar.wait() && rc == SIGNER_OK) rc = fail(SIGNER_ERR_CUDA, "a peer shard failed");
+    return rc;
+}
+
+// after step 3: this shard's ordered W E' sum into its slot; every shard ends up with all N slots
+int shard_gather_corrE(signer_chain *c)
+{
+    ShardLink *L = c->link;
+    ShardShared *S = L->sh;
+    double *slot = c->corrE_all + c->nP * (size_t)L->rank;
+    if (S->emulated) CU(cudaMemsetAsync(c->corrE_all, 0, sizeof(double) * c->nP * (size_t)L->n, c->stream));
+    seg_reduce<<<(unsigned)((c->nP + kPElems - 1) / kPElems), 32 * kPWarps, blocked_sum_smem_bytes(c->n_seg), c->stream>>>(
+        c->corrE_part, c->n_seg, (int)c->nP, slot);
+    c->launches++;
+    ST(check_launch(c->stream, "seg_reduce"));
+    if (S->emulated) return shard_sum<double>(c, c->corrE_all, c->nP * (size_t)L->n);      // the other slots are zero: exact
+    const int rc = S->nccl.AllGather(slot, c->corrE_all, c->nP, kNcclFloat64, S->comms[L->rank], c->stream);   // in place
+    if (rc) return nccl_fail(S, "ncclAllGather", rc);
     return SIGNER_OK;
 }
 
-// column terms of every shard into its part of the global array, all-reduce, tree on every shard
-int shard_loglik(ShardSet &S, int mode_lgm, double *out0)
+// per-genome terms of every shard into its part of the global array, all-reduce, tree on shard 0 (mode_lgm: the
+// constant sum lgamma(M+1), kept by every shard)
+int shard_loglik(signer_chain *c, int mode_lgm, double *out0)
 {
-    std::vector<double *> cols(S.n);
-    for (int g = 0; g < S.n; ++g) {
-        signer_chain *c = S.sh[g];
-        CU(cudaSetDevice(c->device));
-        CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)c->data->n2, c->stream));
-        if (mode_lgm) {
-            LLParams lp{c->I, c->J, c->Jp, 1, c->data->Mrow, c->data->W, nullptr, nullptr, c->col + c->col0, 1, nullptr, 0, nullptr, nullptr, nullptr};
-            loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(1), c->stream>>>(lp);
-            CU(cudaGetLastError());
-        } else {
-            ST(launch_loglik_cols(c));
-        }
-        cols[g] = c->col;
+    CU(cudaMemsetAsync(c->col, 0, sizeof(double) * (size_t)c->data->n2, c->stream));
+    if (mode_lgm) {
+        LLParams lp{c->I, c->J, c->Jp, 1, c->data->Mrow, c->data->W, nullptr, nullptr, c->col + c->col0, 1, nullptr, 0, nullptr, nullptr, nullptr};
+        loglik_cols<<<(c->J + 31) / 32, 32 * kLLWarps, loglik_smem_bytes(1), c->stream>>>(lp);
+        ST(check_launch(c->stream, "loglik_cols"));
+    } else {
+        ST(launch_loglik_cols(c));
     }
-    ST(shard_allreduce<double>(S, cols, (size_t)S.sh[0]->data->n2));
-    for (int g = 0; g < S.n; ++g) {
-        signer_chain *c = S.sh[g];
-        CU(cudaSetDevice(c->device));
-        if (mode_lgm) tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, nullptr, c->data->lgm);
-        else if (g == 0) tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out0);
-        CU(cudaGetLastError());
-    }
-    return SIGNER_OK;
-}
-
-int shard_sync(ShardSet &S)
-{
-    for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); }
-    return SIGNER_OK;
+    ST(shard_sum<double>(c, c->col, (size_t)c->data->n2));
+    if (mode_lgm) tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, nullptr, c->data->lgm);
+    else if (c->link->rank == 0) tree_sum<<<1, 1024, 0, c->stream>>>(c->col, c->data->n2, c->data->lgm, out0);
+    return check_launch(c->stream, "tree_sum");
 }
 
 int sharded_run(const signer_problem *pr, const signer_state *st, const signer_opts *o, signer_outputs *out,
                 const int32_t *devices, int n_dev)
 {
     const int I = pr->I, J = pr->J, K = pr->K;
-    if (n_dev < 1 || n_dev > 64) return fail(SIGNER_ERR_ARG, "sharded run: 1..64 shards");
+    if (n_dev < 1 || n_dev > 32) return fail(SIGNER_ERR_ARG, "sharded run: 1..32 shards");
+    if (o->burn < 0 || o->eval < 0) return fail(SIGNER_ERR_ARG, "burn and eval must be non-negative");
     const int n_seg = (J + kSeg - 1) / kSeg;
     if (n_dev > n_seg) return fail(SIGNER_ERR_ARG, "sharded run: more shards than 32-genome segments");
-    ShardSet S;
-    S.n = n_dev;
-    for (int g = 1; g < n_dev; ++g) if (devices[g] != devices[0]) S.same_device = false;
-    if (!S.same_device) {
+    ShardShared S;
+    S.n = n_dev; S.bar.n = n_dev; S.bufs.assign(n_dev, nullptr);
+    for (int g = 1; g < n_dev; ++g) if (devices[g] != devices[0]) S.emulated = false;
+    if (!S.emulated) {
         for (int a = 0; a < n_dev; ++a) for (int b = a + 1; b < n_dev; ++b)
             if (devices[a] == devices[b]) return fail(SIGNER_ERR_ARG, "sharded run: devices must be all distinct or all the same");
         if (!S.nccl.load()) return fail(SIGNER_ERR_NCCL, "cannot load libnccl.so.2");
         S.comms.assign(n_dev, nullptr);
         std::vector<int> devs(devices, devices + n_dev);
         const int rc = S.nccl.CommInitAll(S.comms.data(), n_dev, devs.data());
-        if (rc) return fail(SIGNER_ERR_NCCL, std::string("ncclCommInitAll: ") + (S.nccl.GetErrorString ? S.nccl.GetErrorString(rc) : "error"));
+        if (rc) return nccl_fail(&S, "ncclCommInitAll", rc);
     }
-    // create the shards
+    // the shards (deleted in reverse order: emulated shards launch on shard 0's stream)
+    std::vector<signer_chain *> sh;
+    std::vector<ShardLink> links(n_dev);
+    struct Cleanup { std::vector<signer_chain *> &v; ~Cleanup() { for (auto it = v.rbegin(); it != v.rend(); ++it) delete *it; } } cleanup{sh};
     for (int g = 0; g < n_dev; ++g) {
         const int s0 = (int)((long long)g * n_seg / n_dev), s1 = (int)((long long)(g + 1) * n_seg / n_dev);
         const int c0 = s0 * kSeg, c1 = std::min(J, s1 * kSeg), Jg = c1 - c0;
         std::shared_ptr<DeviceData> d;
-        ST(upload_data(devices[g], I, Jg, pr->M + (size_t)I * c0, pr->W + (size_t)I * c0, d, c0, J));
+        ST(sgh::get_cohort(devices[g], I, Jg, pr->M + (size_t)I * c0, pr->W + (size_t)I * c0, c0, J, d));
         signer_state sg = *st;
-        sg.Z = nullptr;                                  // the cube (if any) is reduced below, per shard
+        sg.Z = nullptr;                                  // the cube (if any) is reduced by the shard's thread
         sg.E = st->E + (size_t)K * c0; sg.Ae = st->Ae + (size_t)K * c0; sg.Be = st->Be + (size_t)K * c0;
         signer_chain *c = nullptr;
         signer_opts og = *o;
         og.device = devices[g];
         ST(chain_create(d, K, &sg, &og, &c, /*deferred_init=*/true));
-        S.sh.push_back(c);
+        sh.push_back(c);
+        links[g].rank = g; links[g].n = n_dev; links[g].sh = &S;
+        c->link = &links[g];
         c->shard = g; c->n_shards = n_dev; c->col0 = c0;
         ST(dalloc(&c->corrE_all, c->nP * (size_t)n_dev, c->stream));
-        if (S.same_device && g > 0) { CU(cudaStreamSynchronize(c->stream)); c->stream = S.sh[0]->stream; c->borrowed_stream = true; }   // one stream: plain ordering
+        CU(cudaStreamSynchronize(c->stream));
+        if (S.emulated && g > 0) { c->stream = sh[0]->stream; c->borrowed_stream = true; }   // one stream: plain ordering
     }
-    if (S.same_device) { CU(cudaSetDevice(devices[0])); CU(cudaMalloc(&S.ptr_tab, sizeof(void *) * n_dev)); }
-    ST(shard_sync(S));
-    ST(shard_loglik(S, 1, nullptr));                     // sum lgamma(M+1) over the whole cohort, on every shard
-    // initial sufficient statistics and W E'
-    if (st->Z) {
-        for (int g = 0; g < n_dev; ++g) {
-            signer_chain *c = S.sh[g];
-            CU(cudaSetDevice(c->device));
-            ST(reduce_cube(c, st->Z, J, c->col0));
-            c->zcur = 0;
-        }
-        std::vector<int *> zin(n_dev);
-        for (int g = 0; g < n_dev; ++g) zin[g] = S.sh[g]->Zin[0];
-        ST(shard_allreduce<int>(S, zin, S.sh[0]->nP));
-    } else {
-        ST(shard_launch_z(S, o->sweep0, kStZinit, false));
-    }
-    if (!o->Pfixed) { Ops none{0, 0u}; ST(shard_launch_e(S, o->sweep0, none, 1, nullptr)); }
+    if (S.emulated) { CU(cudaSetDevice(devices[0])); CU(cudaMalloc(&S.ptr_tab, sizeof(void *) * n_dev)); }
 
-    const int burn = o->burn, eval = o->eval, keep_par = o->keep_par ? 1 : 0, total = burn + eval;
-    if (burn < 0 || eval < 0) return fail(SIGNER_ERR_ARG, "burn and eval must be non-negative");
-    int cap = 1;
-    if (eval > 0) {
-        for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); ST(ensure_rings(c, eval, keep_par)); cap = c->ring_cap; }
-        for (auto *c : S.sh) cap = std::min(cap, c->ring_cap);
-        signer_chain *c0 = S.sh[0];
-        CU(cudaSetDevice(c0->device));
-        ST(dalloc(&c0->ll_ring, (size_t)eval, c0->stream)); c0->ll_cap = eval;
-    }
-    const bool want_cube = keep_par && out->Zs && eval > 0;
-    if (want_cube) for (auto *c : S.sh) { CU(cudaSetDevice(c->device)); ST(dalloc(&c->Zcube, (size_t)I * c->J * K, c->stream)); }
-
-    auto flush = [&](int r0, int cnt) -> int {            // ring slots 0..cnt-1 hold eval sweeps r0..r0+cnt-1
-        ST(shard_sync(S));
-        signer_chain *c0 = S.sh[0];
-        CU(cudaSetDevice(c0->device));
-        auto cpP = [&](double *dst, const double *src) -> int {
-            if (dst && src) CU(cudaMemcpy(dst + c0->nP * (size_t)r0, src, sizeof(double) * c0->nP * (size_t)cnt, cudaMemcpyDeviceToHost));
-            return SIGNER_OK;
-        };
-        ST(cpP(out->Ps, c0->ring[0].Ps)); ST(cpP(out->Bps, c0->ring[0].Bps)); if (keep_par) ST(cpP(out->Aps, c0->ring[0].Aps));
-        for (auto *c : S.sh) {
-            CU(cudaSetDevice(c->device));
-            auto cpE = [&](double *dst, const double *src) -> int {   // a shard's genomes are a contiguous block of every slice
-                if (dst && src)
-                    CU(cudaMemcpy2D(dst + (size_t)K * J * (size_t)r0 + (size_t)K * c->col0, sizeof(double) * (size_t)K * J, src,
-                                    sizeof(double) * c->nE, sizeof(double) * c->nE, (size_t)cnt, cudaMemcpyDeviceToHost));
-                return SIGNER_OK;
-            };
-            ST(cpE(out->Es, c->ring[0].Es)); ST(cpE(out->Bes, c->ring[0].Bes)); if (keep_par) ST(cpE(out->Aes, c->ring[0].Aes));
-        }
-        return SIGNER_OK;
-    };
-
-    ST(shard_sync(S));
-    const auto t_loop = std::chrono::steady_clock::now();
-    int r0 = 0;
-    for (int k = 0; k < total; ++k) {
-        const uint32_t sweep = o->sweep0 + (uint32_t)k;
-        int order[7];
-        if (o->forced_order) for (int f = 0; f < 7; ++f) order[f] = o->forced_order[(size_t)7 * k + f];
-        else host_perm(o->seed, sweep, order);
-        const SweepPlan pl = plan_sweep(order, o->Pfixed != 0);
-        const bool storing = k >= burn, last = (k == total - 1);
-        const int r = k - burn, slot = storing ? r % cap : 0;
-        std::vector<Slots> slots(S.n);
-        if (storing)
-            for (int g = 0; g < S.n; ++g) {
-                signer_chain *c = S.sh[g]; Ring &rg = c->ring[0];
-                Slots &s = slots[g];
-                s.Es = rg.Es + c->nE * slot; s.Bes = rg.Bes + c->nE * slot; if (keep_par) s.Aes = rg.Aes + c->nE * slot;
-                if (g == 0) { s.Ps = rg.Ps + c->nP * slot; s.Bps = rg.Bps + c->nP * slot; if (keep_par) s.Aps = rg.Aps + c->nP * slot; }
-            }
-        bool storedP = false, storedE = false;
-        for (int t = 0; t < pl.n; ++t) {
-            if (pl.items[t].kind == 1) ST(shard_launch_z(S, sweep, kStZ, want_cube && last));
-            else if (pl.items[t].kind == 2) {
-                for (int g = 0; g < S.n; ++g) {
-                    signer_chain *c = S.sh[g];
-                    CU(cudaSetDevice(c->device));
-                    const Slots *sl = storing ? &slots[g] : nullptr;
-                    ST(launch_p(c, sweep, pl.pops, sl ? sl->Ps : nullptr, sl ? sl->Aps : nullptr, sl ? sl->Bps : nullptr));
-                }
-                storedP = true;
-            } else {
-                ST(shard_launch_e(S, sweep, pl.eops, (pl.has3 && !o->Pfixed) ? 1 : 0, storing ? &slots : nullptr));
-                storedE = true;
-            }
-        }
-        if (storing) {
-            for (int g = 0; g < S.n; ++g) {
-                signer_chain *c = S.sh[g]; const Slots &s = slots[g];
-                CU(cudaSetDevice(c->device));
-                if (!storedP && g == 0) {
-                    CU(cudaMemcpyAsync(s.Ps, c->P, c->nP * 8, cudaMemcpyDeviceToDevice, c->stream));
-                    CU(cudaMemcpyAsync(s.Bps, c->Bp, c->nP * 8, cudaMemcpyDeviceToDevice, c->stream));
-                    if (s.Aps) CU(cudaMemcpyAsync(s.Aps, c->Ap, c->nP * 8, cudaMemcpyDeviceToDevice, c->stream));
-                }
-                if (!storedE) {
-                    CU(cudaMemcpyAsync(s.Es, c->E, c->nE * 8, cudaMemcpyDeviceToDevice, c->stream));
-                    CU(cudaMemcpyAsync(s.Bes, c->Be, c->nE * 8, cudaMemcpyDeviceToDevice, c->stream));
-                    if (s.Aes) CU(cudaMemcpyAsync(s.Aes, c->Ae, c->nE * 8, cudaMemcpyDeviceToDevice, c->stream));
-                }
-            }
-            ST(shard_loglik(S, 0, S.sh[0]->ll_ring + r));
-            if (slot == cap - 1 || last) { ST(flush(r0, slot + 1)); r0 += slot + 1; }
-        }
-    }
-    ST(shard_sync(S));
-    g_loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
-    signer_chain *c0 = S.sh[0];
-    CU(cudaSetDevice(c0->device));
-    if (eval > 0 && (out->loglik || out->bic)) {
-        std::vector<double> ll((size_t)eval);
-        CU(cudaMemcpy(ll.data(), c0->ll_ring, sizeof(double) * (size_t)eval, cudaMemcpyDeviceToHost));
-        const double pen = (double)K * (double)(I + J) * std::log((double)J);
-        for (int r = 0; r < eval; ++r) { if (out->loglik) out->loglik[r] = ll[r]; if (out->bic) out->bic[r] = 2.0 * ll[r] - pen; }
-    }
-    auto cp = [&](void *dst, const void *src, size_t bytes) -> int { if (dst) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return SIGNER_OK; };
-    ST(cp(out->P, c0->P, c0->nP * 8)); ST(cp(out->Ap, c0->Ap, c0->nP * 8)); ST(cp(out->Bp, c0->Bp, c0->nP * 8));
-    ST(cp(out->Zin, c0->Zin[c0->zcur], c0->nP * 4));
-    for (auto *c : S.sh) {
+    // one host thread per shard: initial statistics, then the ordinary sweep loop
+    std::vector<int> rcs(n_dev, SIGNER_OK);
+    std::vector<std::string> errs(n_dev);
+    bool need_lgm = false;                               // a collective: all shards or none
+    for (auto *c : sh) need_lgm |= !c->data->lgm_ready;
+    auto body = [&](int g) -> int {
+        signer_chain *c = sh[g];
         CU(cudaSetDevice(c->device));
+        if (need_lgm) {                                  // sum lgamma(M+1) over the whole cohort, kept by every shard
+            if (is_sharded(c)) ST(shard_loglik(c, 1, nullptr));
+            else ST(ensure_lgm(*c->data));
+        }
+        c->zcur = 0;
+        if (st->Z) {
+            ST(reduce_cube(c, st->Z, J, c->col0));
+            ST(shard_sum<int>(c, c->Zin[0], c->nP));
+        } else {
+            ST(launch_z(c, o->sweep0, kStZinit, nullptr));
+        }
+        if (!o->Pfixed) { Ops none{0, 0u}; ST(launch_e(c, o->sweep0, none, 1, nullptr, nullptr, nullptr)); }
+        // this shard's view of the caller's outputs: its block of genomes; the context-side arrays come from shard 0
+        signer_outputs v = *out;
         const size_t off = (size_t)K * c->col0;
-        ST(cp(out->E ? out->E + off : nullptr, c->E, c->nE * 8)); ST(cp(out->Ae ? out->Ae + off : nullptr, c->Ae, c->nE * 8));
-        ST(cp(out->Be ? out->Be + off : nullptr, c->Be, c->nE * 8)); ST(cp(out->Znj ? out->Znj + off : nullptr, c->Znj[c->zcur], c->nE * 4));
-        if (want_cube)
-            for (int k = 0; k < K; ++k)
-                CU(cudaMemcpy(out->Zs + (size_t)I * J * k + (size_t)I * c->col0, c->Zcube + (size_t)I * c->J * k, sizeof(double) * (size_t)I * c->J,
-                              cudaMemcpyDeviceToHost));
+        if (v.E) v.E += off; if (v.Ae) v.Ae += off; if (v.Be) v.Be += off; if (v.Znj) v.Znj += off;
+        if (g != 0) { v.P = v.Ap = v.Bp = nullptr; v.Zin = nullptr; v.Ps = v.Aps = v.Bps = nullptr; v.loglik = v.bic = nullptr; }
+        return chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, &v);
+    };
+    const auto t_loop = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_dev; ++g)
+        th.emplace_back([&, g]() {
+            rcs[g] = body(g);
+            if (rcs[g] != SIGNER_OK) { errs[g] = g_err; S.bar.abort(); }
+        });
+    for (auto &t : th) t.join();
+    g_loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
+    for (int g = 0; g < n_dev; ++g) {
+        if (rcs[g] == SIGNER_OK) sh[g]->data->lgm_ready = true;   // cached shard cohorts keep their constant
+        if (rcs[g] != SIGNER_OK) return fail(rcs[g], "shard " + std::to_string(g) + ": " + errs[g]);
     }
     return SIGNER_OK;
 }
