@@ -224,12 +224,13 @@ def run_nsig(args):
     for n in range(lo, hi + 1):
         for c in range(args.chains):
             h = list(h0); h[3] = h0[3] / np.sqrt(n)                     # be/sqrt(n), R/signeR.R:163
-            tasks.append(dict(K=n, state=synth.init_state(I, J, n, hyper=dict(be=h[3]), seed=1000 * n + c), hyper=tuple(h),
-                              burn=1000, eval=1000, seed=1000 * n + c))
+            tasks.append(dict(K=n, hyper=tuple(h), burn=args.nsig_burn, eval=args.nsig_eval, seed=1000 * n + c))
 
-    def runner(ts):
+    def runner(ts):                                                      # initial states only for this rank's share
+        for t in ts:
+            t["state"] = synth.init_state(I, J, t["K"], hyper=dict(be=t["hyper"][3]), seed=t["seed"])
         return batch_bics(M, W, ts, devices=[local]) if ts else []
-    runner(tasks[:1])                                                    # warm-up (context, module load)
+    runner([dict(tasks[0], burn=5, eval=5)])                             # warm-up (context, module load, cohort upload)
     dist.barrier()
     t0 = time.perf_counter()
     res = dist.run_tasks_distributed(tasks, runner)
@@ -242,7 +243,7 @@ def run_nsig(args):
         med = {k: float(np.mean(v)) for k, v in med.items()}
         best = max(sorted(med), key=lambda k: med[k])
         print(json.dumps(dict(metric="nsig_sweep_wall_s", value=dt, unit="s", n_gpus=world, higher_is_better=False, scaling="strong",
-                              config=dict(workload=wl, I=I, J=J, nsig=[lo, hi], chains=args.chains, burn=1000, eval=1000, tasks=len(tasks)),
+                              config=dict(workload=wl, I=I, J=J, nsig=[lo, hi], chains=args.chains, burn=args.nsig_burn, eval=args.nsig_eval, tasks=len(tasks)),
                               bic_optimal_nsig=best, median_bic=med, sweeps_per_s=sum(t["burn"] + t["eval"] for t in tasks) / dt)), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -310,10 +311,11 @@ def leg_nsig(M, W, local, lo=2, hi=20, chains=4, burn=1000, ev=1000):
     for n in range(lo, hi + 1):
         for c in range(chains):
             h = list(h0); h[3] = h0[3] / np.sqrt(n)
-            tasks.append(dict(K=n, state=synth.init_state(I, J, n, hyper=dict(be=h[3]), seed=1000 * n + c), hyper=tuple(h),
-                              burn=burn, eval=ev, seed=1000 * n + c))
+            tasks.append(dict(K=n, hyper=tuple(h), burn=burn, eval=ev, seed=1000 * n + c))
 
-    def runner(ts):
+    def runner(ts):                                                      # initial states only for this rank's share
+        for t in ts:
+            t["state"] = synth.init_state(I, J, t["K"], hyper=dict(be=t["hyper"][3]), seed=t["seed"])
         return batch_bics(M, W, ts, devices=[local]) if ts else []
     sgdist.barrier()
     t0 = time.perf_counter()
@@ -396,6 +398,8 @@ def main():
                     help="nsig: wall time of a full nsig model-selection sweep (secondary metric of BASELINE.json)")
     ap.add_argument("--nsig-range", default="2,10")
     ap.add_argument("--chains", type=int, default=1)
+    ap.add_argument("--nsig-burn", type=int, default=1000)
+    ap.add_argument("--nsig-eval", type=int, default=1000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload is None:

@@ -253,32 +253,12 @@ SG_D int binomial_draw(const UStream &s, int kstep, double u_binv, int n, double
         if (u >= r) {
             const double sr = p / q;
             const double a = sr * (nd + 1.0);         // sr*(n-x+1)/x = a/x - sr
-#ifdef SG_NO_SPEC_INV
             double xd = 0.0;
             while (u >= r && x < n) {
                 u = u - r;
                 x += 1; xd += 1.0;
                 r = r * fma(a, rcp_int(x, xd), -sr);
             }
-#else
-            // the search  while (u >= r && x < n) { u -= r; ++x; r *= fma(a, 1/x, -sr); }  four steps at a time: the
-            // reciprocals of the next four x are fetched together and the four steps are evaluated speculatively (same
-            // operations on the same operands in the same order; steps past the stopping point are discarded), so the
-            // table latency leaves the loop-carried chain and the two chains (r and u) overlap
-            for (;;) {
-                const double f1 = fma(a, rcp_int(x + 1, (double)(x + 1)), -sr), f2 = fma(a, rcp_int(x + 2, (double)(x + 2)), -sr);
-                const double f3 = fma(a, rcp_int(x + 3, (double)(x + 3)), -sr), f4 = fma(a, rcp_int(x + 4, (double)(x + 4)), -sr);
-                const double u1 = u - r, r1 = r * f1;
-                const double u2 = u1 - r1, r2 = r1 * f2;
-                const double u3 = u2 - r2, r3 = r2 * f3;
-                const double u4 = u3 - r3, r4 = r3 * f4;
-                if (!(u >= r && x < n)) break;
-                if (!(u1 >= r1 && x + 1 < n)) { x += 1; break; }
-                if (!(u2 >= r2 && x + 2 < n)) { x += 2; break; }
-                if (!(u3 >= r3 && x + 3 < n)) { x += 3; break; }
-                x += 4; u = u4; r = r4;
-            }
-#endif
         }
     } else {
         x = btrs_draw(s, kstep, n, p);

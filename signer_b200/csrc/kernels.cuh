@@ -310,12 +310,6 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
             const int cell = nxt * 32 + lane;
             if (nxt < p.n_batches && cell < p.n_cells) {
                 n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell];
-#ifndef SG_Z_NO_PREFETCH
-                // the next batch's columns of E (cells of one round class are listed genome-major: a few distinct
-                // columns per warp) travel from L2 to L1 while this batch draws
-                const char *en = reinterpret_cast<const char *>(p.E + (size_t)K * col_nxt);
-                sg_prefetch(en); sg_prefetch(en + 8 * K - 8);
-#endif
             }
         }
         SG_ZCLK(1)                                          // staging
@@ -337,7 +331,6 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
 
         SG_ZCLK(2)                                          // direct loop
         // ---- large counts
-        bool claimed_late = false;
         if (__any_sync(kFull, nrem > 0)) {
             // visiting order: counting sort of the classes by d = min(7, expo(S) - expo(P*E)), ties by index
             if (nrem > 0) {
@@ -387,12 +380,6 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
                 z_emit(p, zin_s, row, col, ord[(K - 1) * 32], nrem);
                 nrem = 0;
             }
-            // the chains are done; what is left of this batch is short (at most kNTail draws per cell): claim the
-            // successor now so that the round trip of the claim hides behind the remainder draws
-#ifndef SG_NO_LATE_CLAIM
-            if (!early && lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
-            claimed_late = !early;
-#endif
             // the remainder goes to the unvisited classes by the direct method: the lane's column becomes the
             // cumulative sums in index order with the visited classes zeroed; draw d of a cell uses word d&3 of
             // block kTailBlock0 + (d>>2) of the cell's stream and the same search as the small counts.  The warp
@@ -429,7 +416,7 @@ __global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParam
         if (lane == 0 && t_batch < (1 << 16)) g_z_batch_cycles[t_batch] = (unsigned)(clock64() - t_begin);
 #endif
         if (!early) {
-            if (lane == 0 && !claimed_late) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
+            if (lane == 0) pend = (int)(atomicAdd(p.counter, 1ULL) - p.base);
             nxt = __shfl_sync(kFull, pend, 0);
             const int cell = nxt * 32 + lane;
             if (nxt < p.n_batches && cell < p.n_cells) { n_nxt = p.cell_n[cell]; row_nxt = (int)p.cell_row[cell]; col_nxt = p.cell_col[cell]; }

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -794,7 +795,8 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         if (out->loglik || out->bic) {
             std::vector<double> ll((size_t)eval);
             CU(cudaMemcpy(ll.data(), c->ll_ring, sizeof(double) * (size_t)eval, cudaMemcpyDeviceToHost));
-            const double pen = (double)c->K * (double)(c->I + c->J) * std::log((double)c->J);   // R/cpp_eBayesNMF.R:186
+            const double Jg = (double)c->data->Jglobal;                                          // (a shard: the whole cohort's genomes)
+            const double pen = (double)c->K * ((double)c->I + Jg) * std::log(Jg);               // R/cpp_eBayesNMF.R:186
             for (int r = 0; r < eval; ++r) {
                 if (out->loglik) out->loglik[r] = ll[r];
                 if (out->bic) out->bic[r] = 2.0 * ll[r] - pen;
@@ -878,9 +880,12 @@ struct ShardShared {
     HostBarrier bar;
     std::vector<void *> bufs;        // emulated collectives: this round's buffer of every shard
     void **ptr_tab = nullptr;        // ... and their device table
+    bool keep_comms = false;         // the communicators belong to the process-wide cache
+    HostBarrier start;               // the shards' threads line up before the sweep loop (timing)
+    double loop_ms = 0.0;            // shard 0's sweep loop
     ~ShardShared()
     {
-        for (auto cm : comms) if (cm && nccl.CommDestroy) nccl.CommDestroy(cm);
+        if (!keep_comms) for (auto cm : comms) if (cm && nccl.CommDestroy) nccl.CommDestroy(cm);
         if (ptr_tab) cudaFree(ptr_tab);
     }
 };
@@ -973,16 +978,27 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
     const int n_seg = (J + kSeg - 1) / kSeg;
     if (n_dev > n_seg) return fail(SIGNER_ERR_ARG, "sharded run: more shards than 32-genome segments");
     ShardShared S;
-    S.n = n_dev; S.bar.n = n_dev; S.bufs.assign(n_dev, nullptr);
+    S.n = n_dev; S.bar.n = n_dev; S.start.n = n_dev; S.bufs.assign(n_dev, nullptr);
     for (int g = 1; g < n_dev; ++g) if (devices[g] != devices[0]) S.emulated = false;
+    std::unique_lock<std::mutex> comm_lock;              // communicators are kept per device list and used by one call at a time
     if (!S.emulated) {
         for (int a = 0; a < n_dev; ++a) for (int b = a + 1; b < n_dev; ++b)
             if (devices[a] == devices[b]) return fail(SIGNER_ERR_ARG, "sharded run: devices must be all distinct or all the same");
         if (!S.nccl.load()) return fail(SIGNER_ERR_NCCL, "cannot load libnccl.so.2");
-        S.comms.assign(n_dev, nullptr);
+        // creating communicators (and their first collective) costs tens of milliseconds: keep them for the process
+        static std::mutex mu;
+        static std::map<std::vector<int>, std::vector<nccl_comm_t>> cache;
+        comm_lock = std::unique_lock<std::mutex>(mu);
         std::vector<int> devs(devices, devices + n_dev);
-        const int rc = S.nccl.CommInitAll(S.comms.data(), n_dev, devs.data());
-        if (rc) return nccl_fail(&S, "ncclCommInitAll", rc);
+        auto it = cache.find(devs);
+        if (it == cache.end()) {
+            std::vector<nccl_comm_t> comms(n_dev, nullptr);
+            const int rc = S.nccl.CommInitAll(comms.data(), n_dev, devs.data());
+            if (rc) return nccl_fail(&S, "ncclCommInitAll", rc);
+            it = cache.emplace(devs, comms).first;
+        }
+        S.comms = it->second;
+        S.keep_comms = true;
     }
     // the shards (deleted in reverse order: emulated shards launch on shard 0's stream)
     std::vector<signer_chain *> sh;
@@ -1035,17 +1051,21 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         const size_t off = (size_t)K * c->col0;
         if (v.E) v.E += off; if (v.Ae) v.Ae += off; if (v.Be) v.Be += off; if (v.Znj) v.Znj += off;
         if (g != 0) { v.P = v.Ap = v.Bp = nullptr; v.Zin = nullptr; v.Ps = v.Aps = v.Bps = nullptr; v.loglik = v.bic = nullptr; }
-        return chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, &v);
+        CU(cudaStreamSynchronize(c->stream));
+        if (!S.start.wait()) return fail(SIGNER_ERR_CUDA, "a peer shard failed");
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, &v);
+        if (g == 0) S.loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
     };
-    const auto t_loop = std::chrono::steady_clock::now();
     std::vector<std::thread> th;
     for (int g = 0; g < n_dev; ++g)
         th.emplace_back([&, g]() {
             rcs[g] = body(g);
-            if (rcs[g] != SIGNER_OK) { errs[g] = g_err; S.bar.abort(); }
+            if (rcs[g] != SIGNER_OK) { errs[g] = g_err; S.bar.abort(); S.start.abort(); }
         });
     for (auto &t : th) t.join();
-    g_loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
+    g_loop_ms = S.loop_ms;
     for (int g = 0; g < n_dev; ++g) {
         if (rcs[g] == SIGNER_OK) sh[g]->data->lgm_ready = true;   // cached shard cohorts keep their constant
         if (rcs[g] != SIGNER_OK) return fail(rcs[g], "shard " + std::to_string(g) + ": " + errs[g]);
