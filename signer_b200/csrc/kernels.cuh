@@ -556,8 +556,8 @@ SG_D double blocked_sum_block(const double *a, int n, size_t stride, size_t e0, 
 
 // ------------------------------------------------------------------------------------------------
 // KP  p_family : gibbs_step2/4/6 (src/gibbs_2.cpp:106-120,140-153,172-210) on I x K.
-// A block owns 32 elements.  When step 2 runs, the whole block first adds the W E' segment sums of its elements in the
-// specified order (blocked_sum_block); then warp 0 applies the steps of this sweep, one element per lane.
+// When step 2 runs, the whole block first adds the W E' segment sums of its elements in the specified order
+// (blocked_sum_block, 32 elements at a time); then every warp applies the steps of this sweep to its elements.
 // ------------------------------------------------------------------------------------------------
 struct PParams {
     int IK;
@@ -573,33 +573,42 @@ struct PParams {
     Ops ops;
 };
 
+// PER_WARP elements per warp, kPWarps * PER_WARP per block.
+// The element updates are one long dependent chain per element, and a warp pays for every rare path (a rejected
+// proposal, a ziggurat wedge, the logarithmic acceptance test) that ANY of its lanes takes.  With 32 elements in a warp
+// that is all of them, every time; with two the chain stays near its expected length and the 16 warps of the block
+// interleave on the four schedulers -- the right shape while I*K is a few thousand elements and the kernel is pure
+// latency on the sweep's critical path.  Wide context sets (I*K in the tens of thousands) are throughput-bound
+// instead and use full warps.
+template <int PER_WARP>
 __global__ void __launch_bounds__(32 * kPWarps) p_family(const PParams p)
 {
     extern __shared__ __align__(16) double p_smem[];
-    __shared__ double tot_s[kPElems];
+    constexpr int kBlockElems = kPWarps * PER_WARP;
+    __shared__ double tot_s[kBlockElems];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int e0 = blockIdx.x * kPElems;
+    const size_t e0 = (size_t)blockIdx.x * kBlockElems;
     bool has2 = false;
     for (int o = 0; o < p.ops.n; ++o) has2 |= (p.ops.get(o) == 2);
-    // The element updates are one long dependent chain per element, and a warp pays for every rare path (a rejected
-    // proposal, a ziggurat wedge, the logarithmic acceptance test) that ANY of its lanes takes.  With 32 elements in one
-    // warp that is all of them, every time; two elements per warp keeps the chain near its expected length, and the
-    // 16 warps of the block interleave on the four schedulers.
-    constexpr int kPerWarp = kPElems / kPWarps;
-    const int e = e0 + warp * kPerWarp + lane;
-    const bool mine = lane < kPerWarp && e < p.IK;
-    if (lane >= kPerWarp) prefetch_tables((warp & 1) * 30 + lane - kPerWarp);   // even warps: lines 0..29, odd warps: the rest
+    const size_t eidx = e0 + (size_t)warp * PER_WARP + lane;
+    const bool mine = lane < PER_WARP && eidx < (size_t)p.IK;
+    const int e = (int)eidx;
+    if (PER_WARP < 32) { if (lane >= PER_WARP) prefetch_tables((warp & 1) * 30 + lane - PER_WARP); }   // even warps: lines 0..29, odd warps: the rest
+    else if (warp < 2) prefetch_tables(warp * 32 + lane);
     if (mine) {                                             // what the element updates will want, on its way before the sums
         sg_prefetch(p.P + e); sg_prefetch(p.Ap + e); sg_prefetch(p.Bp + e); sg_prefetch(p.Zin + e);
         sg_prefetch(p.acache.lg1 + e); sg_prefetch(p.acache.lg2 + e); sg_prefetch(p.acache.lg + e);
     }
     if (has2) {
-        const double t = blocked_sum_block(p.corrE_part, p.n_part, (size_t)p.IK, (size_t)e0, (size_t)p.IK, p_smem);
-        if (tid < kPElems) tot_s[tid] = t;
-        __syncthreads();
+        for (int sub = 0; sub < kBlockElems / kPElems; ++sub) {
+            if (e0 + (size_t)sub * kPElems >= (size_t)p.IK) break;
+            const double t = blocked_sum_block(p.corrE_part, p.n_part, (size_t)p.IK, e0 + (size_t)sub * kPElems, (size_t)p.IK, p_smem);
+            if (tid < kPElems) tot_s[sub * kPElems + tid] = t;
+            __syncthreads();                                // the level scratch is reused by the next 32 elements
+        }
     }
     if (!mine) return;
-    const double corrE = has2 ? tot_s[warp * kPerWarp + lane] : 0.0;
+    const double corrE = has2 ? tot_s[warp * PER_WARP + lane] : 0.0;
     double P = p.P[e], Ap = p.Ap[e], Bp = p.Bp[e];
     for (int o = 0; o < p.ops.n; ++o) {
         const int op = p.ops.get(o);
@@ -619,6 +628,7 @@ __global__ void __launch_bounds__(32 * kPWarps) p_family(const PParams p)
     if (p.Aps_slot) p.Aps_slot[e] = Ap;
     if (p.Bps_slot) p.Bps_slot[e] = Bp;
 }
+constexpr int kPWideFrom = 16384;   // I*K from which p_family uses full warps
 inline size_t p_family_smem_bytes(int n_part) { return blocked_sum_smem_bytes(n_part); }
 
 // column sharding: a shard's ordered sum of its own W E' segment sums, into its slot of the gathered buffer
@@ -724,13 +734,23 @@ __device__ long long g_e_clock[4096][5];
 
 __host__ __device__ inline int e_pairs(int K) { return (K + 1) / 2; }
 __host__ __device__ inline int e_groups(int J) { return (J + 31) / 32; }
+// Warps per block.  A round takes one task per warp from at most two column groups (one when the contexts come in
+// chunks).  Wherever a block's range starts inside a column group, pairs + 1 consecutive tasks always lie within two
+// groups, so with at most that many warps a range of one task per warp is done in ONE round; few classes get narrower
+// blocks (and more of them) instead of idle warps.
+inline int e_block_warps(int I, int K)
+{
+    const int np = e_pairs(K);
+    return std::max(1, std::min(kEWarps, I > kERows ? np : (np == 1 ? 2 : np + 1)));
+}
 
+// launched with 32 * e_block_warps(I, K) threads
 __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
 {
     extern __shared__ __align__(128) unsigned char e_smem[];
     __shared__ __align__(8) uint64_t mbar[2];
     double *Ws = reinterpret_cast<double *>(e_smem);        // [2][kERows][kEPitch]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int I = p.I, J = p.J, K = p.K;
     const int npairs = e_pairs(K), n_tasks = e_groups(J) * npairs;
     const int t_begin = (int)((long long)blockIdx.x * n_tasks / gridDim.x), t_end = (int)((long long)(blockIdx.x + 1) * n_tasks / gridDim.x);
@@ -765,7 +785,7 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
 
     for (int base = t_begin; base < t_end;) {
         const int cg0 = base / npairs;
-        const int end = min(t_end, min(base + kEWarps, (cg0 + groups_per_round) * npairs));
+        const int end = min(t_end, min(base + nwarps, (cg0 + groups_per_round) * npairs));
         const int task = base + warp;
         const bool active = task < end;
         const int cg = active ? task / npairs : cg0;

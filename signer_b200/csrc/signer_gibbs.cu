@@ -64,8 +64,10 @@ int ensure_device_setup(int device)
     CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, e_family));             // two W tiles: 51 KB
     CU(cudaFuncSetAttribute(e_family, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-    CU(cudaFuncGetAttributes(&fa, p_family));             // scratch of the ordered W E' sums grows with the number of genomes
-    CU(cudaFuncSetAttribute(p_family, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, p_family<2>));          // scratch of the ordered W E' sums grows with the number of genomes
+    CU(cudaFuncSetAttribute(p_family<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, p_family<32>));
+    CU(cudaFuncSetAttribute(p_family<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, seg_reduce));
     CU(cudaFuncSetAttribute(seg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
 #ifdef SG_Z_CARVEOUT
@@ -152,7 +154,7 @@ struct signer_chain {
     unsigned *ll_ticket = nullptr;               // block counter of loglik_cols' fused tree
     unsigned long long z_launches = 0;
     int z_grid = 0, z_warps = 8, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
-    int e_grid = 1, sms = 1;
+    int e_grid = 1, e_warps = kEWarps, sms = 1;
     Hyper h{};
     Key key{};
     uint32_t sweep0 = 0;
@@ -289,7 +291,8 @@ int launch_p(signer_chain *c, uint32_t sweep, const Ops &ops, double *Ps, double
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 1);
-        p_family<<<(p.IK + kPElems - 1) / kPElems, 32 * kPWarps, p_family_smem_bytes(p.n_part), c->stream>>>(p);
+        if (p.IK >= kPWideFrom) p_family<32><<<(p.IK + 32 * kPWarps - 1) / (32 * kPWarps), 32 * kPWarps, p_family_smem_bytes(p.n_part), c->stream>>>(p);
+        else p_family<2><<<(p.IK + 2 * kPWarps - 1) / (2 * kPWarps), 32 * kPWarps, p_family_smem_bytes(p.n_part), c->stream>>>(p);
     }
     c->launches++;
     ST(check_launch(c->stream, "p_family"));
@@ -310,7 +313,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 2);
-        e_family<<<c->e_grid, kEThreads, kESmemBytes, c->stream>>>(p);
+        e_family<<<c->e_grid, 32 * c->e_warps, kESmemBytes, c->stream>>>(p);
     }
     c->launches++;
     ST(check_launch(c->stream, "e_family"));
@@ -647,7 +650,13 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->z_grid = std::max(1, std::min((c->n_chunks + best_w - 1) / best_w, best_b * sms));
     // e_family: every block takes a contiguous range of warp tasks (column group x class pair); all blocks resident in one wave
     c->sms = sms;
-    c->e_grid = std::max(1, std::min(3 * sms, (e_groups(c->J) * e_pairs(K) + kEWarps - 1) / kEWarps));
+    c->e_warps = e_block_warps(c->I, K);
+    {
+        int per_sm = 0;                                   // resident blocks of this width (two 26 KB tiles each)
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family, 32 * c->e_warps, kESmemBytes));
+        const int n_tasks = e_groups(c->J) * e_pairs(K);
+        c->e_grid = std::max(1, std::min(std::max(1, per_sm) * sms, (n_tasks + c->e_warps - 1) / c->e_warps));   // one round per block where they all fit
+    }
     if (p_family_smem_bytes(c->n_seg) > (size_t)g_z_dyn_smem_max[c->device])
         return fail(SIGNER_ERR_ARG, "too many genomes for one device: the W E' sums do not fit the reduction's shared memory; shard the columns");
 
@@ -1275,7 +1284,7 @@ int signer_gibbs_batch(int32_t I, int32_t J, const double *M, const double *W, s
     std::vector<int> rcs(n_devices, SIGNER_OK);
     // small cohorts are launch-latency bound: run several chains per device concurrently (own streams)
     const long long cells = (long long)I * J;
-    const int tpd = cells <= 250000 ? 4 : (cells <= 2000000 ? 2 : 1);
+    const int tpd = cells <= 250000 ? 8 : (cells <= 2000000 ? 2 : 1);
     std::vector<std::shared_ptr<DeviceData>> datas(n_devices);
     std::vector<std::atomic<int>> next(n_devices);
     std::vector<std::mutex> mus(n_devices);
