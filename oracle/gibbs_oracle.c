@@ -471,7 +471,7 @@ static void multinomial_cell(uint64_t seed, uint32_t sweep, uint32_t stream, int
     ustream us; us_init(&us, seed, sweep, stream, (uint32_t)(s + I * g));
     if (n <= NDIRECT) {
         /* per-count algorithm switch: small counts use the direct method -- n categorical draws,
-         * draw t from half (t&1) of block (t>>1): class = first k with u*S < cumulative sum */
+         * draw t from word (t&3) of block (t>>2): class = first k < K-1 with u*S < cumulative sum, else K-1 */
         for (int t = 0; t < n; t++) {
             double uq[4];
             us_quad(&us, (uint32_t)t >> 2, uq);
@@ -761,6 +761,38 @@ int oracle_gibbs_run(int I, int J, int K, const double *M, const double *W, cons
     if (Znj_out) cube_sum_i_t(&c, Znj_out);
     free(c.Z);
     return 0;
+}
+
+/* R's rmultinom LITERALLY (nmath/rmultinom.c as SURVEY.md Appendix C restates it): classes in index order, no re-ordering,
+ * no early stop, no direct method -- for k < K-1: skip zero probabilities; pp = prob[k] / p_tot; rN[k] = pp < 1 ?
+ * rbinom(n, pp) : n; n -= rN[k]; stop when n <= 0; p_tot -= prob[k]; the last class takes the remainder.  prob = the
+ * reference's Fi = P[s,k] E[k,g] / (PE)[s,g] (src/gibbs_2.cpp:89-93).  The binomials are this file's binomial_draw on
+ * the cell's stream (conditional binomial k takes word k&3 of block k>>2).  NOT the algorithm of the draw specification:
+ * it exists so that the specification's re-ordered chain + direct remainder (and the CUDA kernel) can be cross-checked
+ * statistically against the structure R actually uses. */
+void oracle_multinomial_cell_literal(uint64_t seed, uint32_t sweep, uint32_t stream, int I, int K,
+                                     int s, int g, double Mval, const double *P, const double *E, double *z /* K */)
+{
+    for (int m = 0; m < K; m++) z[m] = 0.0;
+    int n = (int)Mval;
+    if (n <= 0) return;
+    double S = 0.0;
+    for (int m = 0; m < K; m++) S = fma(P[s + (size_t)I * m], E[m + (size_t)K * g], S);
+    if (!(S > 0.0) || !(S <= 1.7976931348623157e308)) { z[K - 1] = (double)n; return; }
+    ustream us; us_init(&us, seed, sweep, stream, (uint32_t)(s + I * g));
+    long double p_tot = 1.0L;
+    for (int m = 0; m < K - 1; m++) {
+        double prob = (P[s + (size_t)I * m] * E[m + (size_t)K * g]) / S;
+        if (prob != 0.0) {
+            double pp = (double)((long double)prob / p_tot);
+            int zz = (pp < 1.0) ? ((pp > 0.0) ? binomial_draw(&us, m, n, pp) : 0) : n;
+            z[m] = (double)zz;
+            n -= zz;
+        }
+        if (n <= 0) return;
+        p_tot -= (long double)prob;
+    }
+    z[K - 1] = (double)n;
 }
 
 /* teacher-forced single cell for unit tests */

@@ -52,6 +52,8 @@ def lib():
         L.oracle_loglik.argtypes = [i32, i32, i32, dp, dp, dp, dp]
         L.oracle_multinomial_cell.restype = None
         L.oracle_multinomial_cell.argtypes = [u64, u32, u32, i32, i32, i32, i32, d, dp, dp, dp]
+        L.oracle_multinomial_cell_literal.restype = None
+        L.oracle_multinomial_cell_literal.argtypes = [u64, u32, u32, i32, i32, i32, i32, d, dp, dp, dp]
         L.oracle_gibbs_run.restype = i32
         L.oracle_gibbs_run.argtypes = ([i32, i32, i32, dp, dp, dp] + [dp] * 6 + [dp, i32, i32, i32, i32,
                                        u64, u32, i32, C.POINTER(i32)] + [dp] * 10)
@@ -93,6 +95,15 @@ def multinomial_cell(seed, sweep, stream, s, g, Mval, P, E):
     I, K = P.shape
     z = np.zeros(K)
     lib().oracle_multinomial_cell(seed, sweep, stream, I, K, s, g, float(Mval), _p(P), _p(E), _p(z))
+    return z
+
+
+def multinomial_cell_literal(seed, sweep, stream, s, g, Mval, P, E):
+    """R's rmultinom structure literally (k ascending, no early stop) -- see oracle_multinomial_cell_literal."""
+    P, E = _f(P), _f(E)
+    I, K = P.shape
+    z = np.zeros(K)
+    lib().oracle_multinomial_cell_literal(seed, sweep, stream, I, K, s, g, float(Mval), _p(P), _p(E), _p(z))
     return z
 
 

@@ -84,21 +84,29 @@ def test_gamma_and_binomial_moments_on_device(sg):
 
 
 def test_ebayesnmf_and_model_selection_breast21(sg):
-    """Config 1 (the vignette data): the host mirror end to end.  The reference's only result-level
-    statement is a figure caption ('the optimal number of signatures for this dataset is 5',
-    vignettes/signeR-vignette.Rhtml:400) -- a soft anchor: assert the optimum lies in 3..7 and that
-    the BIC curve rises from n=2 to the optimum."""
+    """Config 1 (the vignette data): the host mirror end to end with the reference's defaults -- set.seed(42)
+    (vignettes/signeR-vignette.Rhtml:78), start = 'lee', testing_burn = testing_eval = 1000 (R/signeR.R:66).  The
+    reference's only result-level statement is a figure caption: 'the optimal number of signatures for this dataset
+    is 5' (vignettes/signeR-vignette.Rhtml:400).  Single chains of this posterior get trapped in local modes (n = 4, 5
+    and 6 lie within ~50 BIC units of each other across seeds), so besides the seed-42 run the test takes the best
+    median BIC per candidate over four seeds: both must name 5."""
     M, W, _ = synth.breast21()
-    sg.set_seed(42)
-    rng = np.random.default_rng(42)
-    res = sg.signeR(M.T, samples="rows", Opport=W, nlim=(2, 8), try_all=True, start="random",
-                    testing_burn=400, testing_eval=300, main_burn=500, main_eval=200, rng=rng)
+    runs = {}
+    for seed in (42, 1, 2, 3):
+        sg.set_seed(seed)
+        runs[seed] = sg.signeR(M.T, samples="rows", Opport=W, nlim=(2, 8), try_all=True, start="lee", testing_burn=1000,
+                               testing_eval=1000, main_burn=500, main_eval=200, rng=np.random.default_rng(seed))
+    res = runs[42]
     assert res["tested_n"] == [2, 3, 4, 5, 6, 7, 8]
     med = [float(np.median(b)) for b in res["Test_BICs"]]
     nopt = res["Nsign"]
     assert nopt == res["tested_n"][int(np.argmax(med))]           # plain argmax of the median BIC agrees with the replayed rule
-    _report(breast21_nopt=int(nopt), breast21_median_bics=med)
-    assert 3 <= nopt <= 7, (nopt, med)
+    best = np.max([[float(np.median(b)) for b in r["Test_BICs"]] for r in runs.values()], axis=0)
+    _report(breast21_nopt_seed42=int(nopt), breast21_median_bics_seed42=med, breast21_nopt_by_seed={str(k): int(v["Nsign"]) for k, v in runs.items()},
+            breast21_best_median_bic_per_n=best.tolist())
+    assert nopt == 5, (nopt, med)
+    assert res["tested_n"][int(np.argmax(best))] == 5, best
+    assert all(3 <= r["Nsign"] <= 7 for r in runs.values())
     assert med[res["tested_n"].index(nopt)] > med[0]
     Phat, Ehat = res["Phat"], res["Ehat"]
     assert Phat.shape == (96, nopt) and Ehat.shape == (nopt, 21)
