@@ -679,7 +679,8 @@ constexpr int kEThreads = 32 * kEWarps;
 constexpr int kERows = 96;        // contexts per staged chunk of W
 constexpr int kEPitch = 34;       // doubles per staged row: 272 B keeps every row 16-byte aligned for the bulk copies; lanes
                                   // that walk down a column (pass 2) meet two-way bank conflicts only
-constexpr size_t kESmemBytes = sizeof(double) * 2 * kERows * kEPitch;
+__host__ __device__ constexpr int e_slots(int maxw) { return maxw == 8 ? 2 : 4; }
+inline size_t e_smem_bytes(int maxw) { return sizeof(double) * e_slots(maxw) * kERows * kEPitch; }
 
 SG_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 SG_D void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -738,33 +739,44 @@ __host__ __device__ inline int e_groups(int J) { return (J + 31) / 32; }
 // chunks).  Wherever a block's range starts inside a column group, pairs + 1 consecutive tasks always lie within two
 // groups, so with at most that many warps a range of one task per warp is done in ONE round; few classes get narrower
 // blocks (and more of them) instead of idle warps.
+constexpr int kEWarpsWide = 16;
 inline int e_block_warps(int I, int K)
 {
     const int np = e_pairs(K);
-    return std::max(1, std::min(kEWarps, I > kERows ? np : (np == 1 ? 2 : np + 1)));
+    if (I > kERows) return std::max(1, std::min(kEWarpsWide, np));
+    return std::max(1, std::min(kEWarps, np == 1 ? 2 : np + 1));
 }
 
-// launched with 32 * e_block_warps(I, K) threads
-__global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
+// launched with 32 * e_block_warps(I, K) threads.  MAXW = 8: contexts fit one tile (three blocks per SM); MAXW = 16: the
+// contexts stream through in chunks, and one block takes ALL class pairs of a column group in one round (up to 16
+// warps), so that the tile is streamed once per pass instead of once per pass and round
+template <int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const EParams p)
 {
+    constexpr int NS = e_slots(MAXW);                       // tile slots: two column groups, or a ring of context chunks
     extern __shared__ __align__(128) unsigned char e_smem[];
-    __shared__ __align__(8) uint64_t mbar[2];
-    double *Ws = reinterpret_cast<double *>(e_smem);        // [2][kERows][kEPitch]
+    __shared__ __align__(8) uint64_t mbar[NS];
+    double *Ws = reinterpret_cast<double *>(e_smem);        // [NS][kERows][kEPitch]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int I = p.I, J = p.J, K = p.K;
     const int npairs = e_pairs(K), n_tasks = e_groups(J) * npairs;
-    const int t_begin = (int)((long long)blockIdx.x * n_tasks / gridDim.x), t_end = (int)((long long)(blockIdx.x + 1) * n_tasks / gridDim.x);
+    const int nchunks = (I + kERows - 1) / kERows;
+    // contiguous range of tasks; chunked contexts: whole column groups (a round cannot leave its group there)
+    const int unit = nchunks == 1 ? 1 : npairs, n_units = n_tasks / unit;
+    const int t_begin = (int)((long long)blockIdx.x * n_units / gridDim.x) * unit, t_end = (int)((long long)(blockIdx.x + 1) * n_units / gridDim.x) * unit;
     bool has3 = false;
     for (int o = 0; o < p.ops.n; ++o) has3 |= (p.ops.get(o) == 3);
     const bool need_w = has3 || p.do_corrE;
-    const int nchunks = (I + kERows - 1) / kERows;
     const int groups_per_round = nchunks == 1 ? 2 : 1;
     if (tid == 0) {
-        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    unsigned nload0 = 0, nload1 = 0;                        // tiles sent into each slot so far (uniform over the block)
+    unsigned nload[NS];                                     // tiles sent into each slot so far (uniform over the block)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) nload[s] = 0;
     prefetch_tables(tid - 32);
     SG_ECLK(0)
 
@@ -779,9 +791,19 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
             const double *src = p.W + (size_t)r0 * p.Jp + (size_t)cg * 32;
             for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (size_t)r * kEPitch, src + (size_t)r * p.Jp, 256u, bar);
         }
-        if (slot == 0) ++nload0; else ++nload1;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) if (s == slot) ++nload[s];
     };
-    auto wait_tile = [&](int slot) { mbar_wait(&mbar[slot], ((slot == 0 ? nload0 : nload1) - 1u) & 1u); };
+    auto wait_tile = [&](int slot) {
+        unsigned n = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) if (s == slot) n = nload[s];
+        mbar_wait(&mbar[slot], (n - 1u) & 1u);
+    };
+    // chunked contexts: the first NS chunks of column group cg go out
+    auto start_stream = [&](int cg) {
+        for (int c = 0; c < NS && c < nchunks; ++c) send_tile(c, cg, c * kERows);
+    };
 
     for (int base = t_begin; base < t_end;) {
         const int cg0 = base / npairs;
@@ -801,8 +823,7 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
                 send_tile(0, cg0, 0);
                 if ((end - 1) / npairs > cg0) send_tile(1, cg0 + 1, 0);
             } else {
-                send_tile(0, cg0, 0);
-                send_tile(1, cg0, kERows);
+                start_stream(cg0);
             }
         }
         if (jin && p.ops.n) {                               // the element state is wanted after pass 1: start bringing it in
@@ -813,22 +834,46 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
         double acc0 = 0.0, acc1 = 0.0;
         if (has3) {
             for (int c = 0; c < nchunks; ++c) {
-                const int slot = nchunks == 1 ? cg - cg0 : (c & 1);
+                const int slot = nchunks == 1 ? cg - cg0 : (c % NS);
                 const int r0 = c * kERows, rows = min(kERows, I - r0);
                 if (active) {
-                    wait_tile(slot);
                     const double *Wt = Ws + (size_t)slot * kERows * kEPitch + lane;
                     const double *P0 = p.P + (size_t)I * ka + r0, *P1 = p.P + (size_t)I * kb + r0;
+                    if (MAXW == 8) {                        // I*K*8 bytes of P stay in L1: warp-uniform loads
+                        wait_tile(slot);
 #pragma unroll 8
-                    for (int r = 0; r < rows; ++r) {
-                        const double w = Wt[r * kEPitch];
-                        acc0 = fma(__ldg(P0 + r), w, acc0);
-                        acc1 = fma(__ldg(P1 + r), w, acc1);
+                        for (int r = 0; r < rows; ++r) {
+                            const double w = Wt[r * kEPitch];
+                            acc0 = fma(__ldg(P0 + r), w, acc0);
+                            acc1 = fma(__ldg(P1 + r), w, acc1);
+                        }
+                    } else {
+                        // wide context sets: P does not fit L1 next to the tiles.  The chunk's 96 rows of the two classes are
+                        // read coalesced into registers (three rows per lane and class, on their way while the tile
+                        // arrives) and handed round by shuffle
+                        double pa[3], pb[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const int r = 32 * q + lane;
+                            pa[q] = r < rows ? __ldg(P0 + r) : 0.0;
+                            pb[q] = r < rows ? __ldg(P1 + r) : 0.0;
+                        }
+                        wait_tile(slot);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const int nr = min(32, rows - 32 * q);
+#pragma unroll 8
+                            for (int l = 0; l < nr; ++l) {
+                                const double w = Wt[(32 * q + l) * kEPitch];
+                                acc0 = fma(__shfl_sync(kFull, pa[q], l), w, acc0);
+                                acc1 = fma(__shfl_sync(kFull, pb[q], l), w, acc1);
+                            }
+                        }
                     }
                 }
                 if (nchunks > 1) {
                     __syncthreads();                        // the slot is free again
-                    if (c + 2 < nchunks) send_tile(slot, cg0, (c + 2) * kERows);
+                    if (c + NS < nchunks) send_tile(slot, cg0, (c + NS) * kERows);
                 }
             }
         }
@@ -851,12 +896,9 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
         SG_ECLK(2)
         if (!p.do_corrE) { base = end; continue; }
         // ---- pass 2: W E' of this segment for (ka, kb): lanes = contexts, E by shuffle, fma chain in genome order
-        if (nchunks > 1 && has3) {                          // restart the stream of chunks
-            send_tile(0, cg0, 0);
-            send_tile(1, cg0, kERows);
-        }
+        if (nchunks > 1 && has3) start_stream(cg0);         // restart the stream of chunks
         for (int c = 0; c < nchunks; ++c) {
-            const int slot = nchunks == 1 ? cg - cg0 : (c & 1);
+            const int slot = nchunks == 1 ? cg - cg0 : (c % NS);
             const int r0 = c * kERows, rows = min(kERows, I - r0);
             if (active) {
                 wait_tile(slot);
@@ -885,7 +927,7 @@ __global__ void __launch_bounds__(kEThreads, 3) e_family(const EParams p)
             }
             if (nchunks > 1) {
                 __syncthreads();
-                if (c + 2 < nchunks) send_tile(slot, cg0, (c + 2) * kERows);
+                if (c + NS < nchunks) send_tile(slot, cg0, (c + NS) * kERows);
             }
         }
         SG_ECLK(3)

@@ -62,8 +62,10 @@ int ensure_device_setup(int device)
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
     CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (33 K + 3264) bytes: above 48 KB from K = 88 (K <= 128 is accepted)
     CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-    CU(cudaFuncGetAttributes(&fa, e_family));             // two W tiles: 51 KB
-    CU(cudaFuncSetAttribute(e_family, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, e_family<kEWarps>));    // two W tiles: 51 KB
+    CU(cudaFuncSetAttribute(e_family<kEWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, e_family<kEWarpsWide>));
+    CU(cudaFuncSetAttribute(e_family<kEWarpsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, p_family<2>));          // scratch of the ordered W E' sums grows with the number of genomes
     CU(cudaFuncSetAttribute(p_family<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, p_family<32>));
@@ -171,6 +173,7 @@ struct signer_chain {
     Ring ring[2];
     int ring_cap = 0, ring_keep = 0;
     int last_eval = 0;
+    double last_enqueue_ms = 0.0;            // host time the last run spent enqueuing its sweeps (before waiting for the device)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];
 
@@ -313,7 +316,8 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 2);
-        e_family<<<c->e_grid, 32 * c->e_warps, kESmemBytes, c->stream>>>(p);
+        if (c->I > kERows) e_family<kEWarpsWide><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarpsWide), c->stream>>>(p);
+        else e_family<kEWarps><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarps), c->stream>>>(p);
     }
     c->launches++;
     ST(check_launch(c->stream, "e_family"));
@@ -653,9 +657,11 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->e_warps = e_block_warps(c->I, K);
     {
         int per_sm = 0;                                   // resident blocks of this width (two 26 KB tiles each)
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family, 32 * c->e_warps, kESmemBytes));
+        if (c->I > kERows) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family<kEWarpsWide>, 32 * c->e_warps, e_smem_bytes(kEWarpsWide)));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family<kEWarps>, 32 * c->e_warps, e_smem_bytes(kEWarps)));
         const int n_tasks = e_groups(c->J) * e_pairs(K);
-        c->e_grid = std::max(1, std::min(std::max(1, per_sm) * sms, (n_tasks + c->e_warps - 1) / c->e_warps));   // one round per block where they all fit
+        const int want = c->I > kERows ? e_groups(c->J) : (n_tasks + c->e_warps - 1) / c->e_warps;   // chunked contexts: whole column groups per block
+        c->e_grid = std::max(1, std::min(std::max(1, per_sm) * sms, want));   // one round per block where they all fit
     }
     if (p_family_smem_bytes(c->n_seg) > (size_t)g_z_dyn_smem_max[c->device])
         return fail(SIGNER_ERR_ARG, "too many genomes for one device: the W E' sums do not fit the reduction's shared memory; shard the columns");
@@ -739,6 +745,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     Joiner drain{[c, out]() { if (out) { TransferPool &p = TransferPool::of(c->device); p.wait(c->ring[0].inflight); p.wait(c->ring[1].inflight); } }};
     GroupPtr cube_group = sgh::make_group();
     Joiner drain_cube{[c, &cube_group]() { TransferPool::of(c->device).wait(cube_group); }};
+    const auto t_enqueue = std::chrono::steady_clock::now();
     for (int k = 0; k < total; ++k) {
         const uint32_t sweep = c->sweep0 + (uint32_t)c->sweeps_done;
         int order[7];
@@ -777,6 +784,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         c->sweeps_done++;
     }
     ST(wait_loglik(c));                                    // the launching stream ends after the last log-likelihood
+    c->last_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enqueue).count();
     c->last_eval = eval;
     if (eval > 0 && do_stats) { c->stats_valid = true; c->stats_np = (double)c->nP * eval; c->stats_ne = (double)c->nE * eval; }
     if (out && eval > 0) {
@@ -1062,9 +1070,22 @@ int sharded_run(const signer_problem *pr, const signer_state *st, const signer_o
         if (g != 0) { v.P = v.Ap = v.Bp = nullptr; v.Zin = nullptr; v.Ps = v.Aps = v.Bps = nullptr; v.loglik = v.bic = nullptr; }
         CU(cudaStreamSynchronize(c->stream));
         if (!S.start.wait()) return fail(SIGNER_ERR_CUDA, "a peer shard failed");
+        static const bool trace = [] { const char *e = std::getenv("SIGNER_TRACE"); return e && e[0] == '1'; }();
+        if (trace) c->profiling = true;                  // events around every kernel of this shard
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = chain_run(c, o->burn, o->eval, o->keep_par, o->forced_order, &v);
-        if (g == 0) S.loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (g == 0) S.loop_ms = ms;
+        if (trace && rc == SIGNER_OK) {                  // where a sharded sweep spends its time: device time per kernel class vs the loop's wall time
+            double kms[4] = {0, 0, 0, 0};
+            long long kn[4] = {0, 0, 0, 0};
+            signer_chain_profile(c, 0, kms, (int64_t *)kn);
+            const int nsw = std::max(1, o->burn + o->eval);
+            std::fprintf(stderr, "[sharded] shard %d/%d (device %d, %d genomes): loop %.3f ms/sweep, host enqueue %.3f ms/sweep; kernels per sweep: "
+                         "z_alloc_fused %.3f, p_family %.3f, e_family %.3f ms (sum %.3f); exchanges + waiting for peers + gaps %.3f ms\n",
+                         g, n_dev, c->device, c->J, ms / nsw, c->last_enqueue_ms / nsw, kms[0] / nsw, kms[1] / nsw, kms[2] / nsw,
+                         (kms[0] + kms[1] + kms[2]) / nsw, ms / nsw - (kms[0] + kms[1] + kms[2]) / nsw);
+        }
         return rc;
     };
     std::vector<std::thread> th;
