@@ -23,6 +23,9 @@ struct DeviceData {
     double *W = nullptr;       // [I][Jp]
     double *lgm = nullptr;     // sum lgamma(M+1), one double (filled by the caller: needs the log-likelihood kernel)
     bool lgm_ready = false;
+    // TMA descriptor of W ([I][Jp] f64; box = 34 genomes x 96 contexts) for e_family's tile loads, made on first use
+    alignas(64) unsigned char wmap[128] = {0};
+    bool wmap_ready = false;
     size_t bytes = 0;          // device memory held
     ~DeviceData();
 };

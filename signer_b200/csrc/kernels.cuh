@@ -17,6 +17,8 @@
 // coalesced rows, the W E' pass uses 128-bit loads.  z_alloc_fused does not read M: it walks a
 // count-sorted list of the non-zero cells built once per cohort (see K1).
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched from the driver at run time)
+
 #include "draws.cuh"
 
 namespace sg {
@@ -672,6 +674,7 @@ struct EParams {
     Key key;
     uint32_t sweep;
     Ops ops;
+    CUtensorMap wmap;           // W as a 2-D tensor [I][Jp], box = kEPitch genomes x kERows contexts
 };
 
 constexpr int kEWarps = 8;
@@ -680,7 +683,7 @@ constexpr int kERows = 96;        // contexts per staged chunk of W
 constexpr int kEPitch = 34;       // doubles per staged row: 272 B keeps every row 16-byte aligned for the bulk copies; lanes
                                   // that walk down a column (pass 2) meet two-way bank conflicts only
 __host__ __device__ constexpr int e_slots(int maxw) { return maxw == 8 ? 2 : 4; }
-inline size_t e_smem_bytes(int maxw) { return sizeof(double) * e_slots(maxw) * kERows * kEPitch; }
+inline size_t e_smem_bytes(int maxw) { return sizeof(double) * e_slots(maxw) * kERows * kEPitch + 128; }
 
 SG_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 SG_D void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -693,11 +696,12 @@ SG_D void mbar_wait(uint64_t *bar, uint32_t parity)
     asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted in bytes on the mbarrier
-SG_D void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+// TMA: one box of the 2-D tensor (x = first genome, y = first context) into shared memory, completion counted in bytes on
+// the mbarrier; rows and columns beyond the tensor arrive as zeros (and count)
+SG_D void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
 // inlined: the kernel's parameters are read from the constant bank (a call by reference would copy them to the stack,
@@ -751,12 +755,13 @@ inline int e_block_warps(int I, int K)
 // contexts stream through in chunks, and one block takes ALL class pairs of a column group in one round (up to 16
 // warps), so that the tile is streamed once per pass instead of once per pass and round
 template <int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const EParams p)
+__global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const __grid_constant__ EParams p)
 {
     constexpr int NS = e_slots(MAXW);                       // tile slots: two column groups, or a ring of context chunks
     extern __shared__ __align__(128) unsigned char e_smem[];
     __shared__ __align__(8) uint64_t mbar[NS];
-    double *Ws = reinterpret_cast<double *>(e_smem);        // [NS][kERows][kEPitch]
+    // [NS][kERows][kEPitch]; TMA wants its destination 128-byte aligned (a slot is 204 x 128 bytes)
+    double *Ws = reinterpret_cast<double *>(e_smem + ((128u - (smem_u32(e_smem) & 127u)) & 127u));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int I = p.I, J = p.J, K = p.K;
     const int npairs = e_pairs(K), n_tasks = e_groups(J) * npairs;
@@ -780,16 +785,14 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const E
     prefetch_tables(tid - 32);
     SG_ECLK(0)
 
-    // warp 0 sends rows [r0, r0 + rows) of column group cg into `slot`
+    // thread 0 sends contexts [r0, r0 + kERows) of column group cg into `slot`: ONE request to the TMA unit (the box is
+    // kEPitch = 34 genomes wide, so the tile lands with the padded pitch; a request per 256-byte row, as in the first
+    // version of this kernel, kept the unit busy for ~20 k cycles per block: it is bound by requests, not bytes)
     auto send_tile = [&](int slot, int cg, int r0) {
-        const int rows = min(kERows, I - r0);
-        if (warp == 0) {
+        if (tid == 0) {
             uint64_t *bar = &mbar[slot];
-            if (lane == 0) mbar_expect_tx(bar, (uint32_t)rows * 256u);
-            __syncwarp();
-            double *dst = Ws + (size_t)slot * kERows * kEPitch;
-            const double *src = p.W + (size_t)r0 * p.Jp + (size_t)cg * 32;
-            for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (size_t)r * kEPitch, src + (size_t)r * p.Jp, 256u, bar);
+            mbar_expect_tx(bar, (uint32_t)(kERows * kEPitch * sizeof(double)));
+            tma_load_2d(Ws + (size_t)slot * kERows * kEPitch, &p.wmap, cg * 32, r0, bar);
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) if (s == slot) ++nload[s];

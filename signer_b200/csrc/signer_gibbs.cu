@@ -100,6 +100,36 @@ int ensure_lgm(DeviceData &d)
     return SIGNER_OK;
 }
 
+// The TMA descriptor of W for e_family (kernels.cuh).  cuTensorMapEncodeTiled is a driver entry point: fetched through the
+// runtime, so the library links against libcudart only.
+std::mutex g_wmap_mu;
+int ensure_wmap(DeviceData &d)
+{
+    std::lock_guard<std::mutex> lk(g_wmap_mu);
+    if (d.wmap_ready) return SIGNER_OK;
+    typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SIGNER_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (encode_t)fn;
+    }
+    static_assert(sizeof(CUtensorMap) <= sizeof(d.wmap), "descriptor storage");
+    CU(cudaSetDevice(d.device));
+    const cuuint64_t dims[2] = {(cuuint64_t)d.Jp, (cuuint64_t)d.I};               // fastest first: genomes, contexts
+    const cuuint64_t strides[1] = {(cuuint64_t)d.Jp * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)kEPitch, (cuuint32_t)kERows}, estr[2] = {1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap *>(d.wmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d.W, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SIGNER_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    d.wmap_ready = true;
+    return SIGNER_OK;
+}
+
 int upload_data(int device, int I, int J, const double *M, const double *W, std::shared_ptr<DeviceData> &out, int col0 = 0,
                 int Jglobal = -1)
 {
@@ -313,6 +343,7 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     p.Es_slot = Es; p.Aes_slot = Aes; p.Bes_slot = Bes;
     p.acache = ACache{c->acache_e, c->acache_e + c->nE, c->acache_e + 2 * c->nE};
     p.h = c->h; p.key = c->key; p.sweep = sweep; p.ops = ops;
+    std::memcpy(&p.wmap, c->data->wmap, sizeof(CUtensorMap));
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 2);
@@ -581,6 +612,7 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     if (!st->P || !st->E || !st->Ap || !st->Bp || !st->Ae || !st->Be) return fail(SIGNER_ERR_ARG, "state: P,E,Ap,Bp,Ae,Be must be non-null");
     CU(cudaSetDevice(data->device));
     ST(ensure_device_setup(data->device));
+    ST(ensure_wmap(*data));
     std::unique_ptr<signer_chain> c(new signer_chain());
     c->data = data; c->device = data->device; c->I = data->I; c->J = data->J; c->Jp = data->Jp; c->K = K;
     c->nP = (size_t)c->I * K; c->nE = (size_t)K * c->J;
