@@ -456,10 +456,10 @@ SG_D double update_b(Key key, uint32_t sweep, uint32_t stream, uint32_t e, doubl
 // in a per-element cache: A changes only when a proposal is accepted, and then its terms are exactly the
 // y-terms just evaluated.  Same operations on the same operands, so the result is bit-identical to
 // re-evaluating them (which is what the oracle does).
-struct ACache { double *lg1, *lg2, *lg; };     // lgamma(A+1), lgamma(A*A/var), log(A)
+struct ACache { double *lg1, *lg2, *lg; };     // lgamma(A+1), lgamma(A*A/var), log(A): loaded and stored by the caller of update_a
 
 SG_D double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, double A, double X, double B, double l, double var,
-                                        const ACache c, size_t ci)
+                                        double &c_lg1, double &c_lg2, double &c_lg)
 {
     UStream us; us.init(key, sweep, stream, e);
     const double shape = (A * A) / var;
@@ -468,16 +468,16 @@ SG_D double update_a(Key key, uint32_t sweep, uint32_t stream, uint32_t e, doubl
     const double y = (kTiny < g) ? g : kTiny;
     const double lgy1 = det_lgamma(y + 1), lgy2 = det_lgamma((y * y) / var), logy = det_log(y);
     const double lnp = (y - A) * (det_log(B) + det_log(X) - l)
-                     + c.lg1[ci] - lgy1
-                     + c.lg2[ci] - lgy2
+                     + c_lg1 - lgy1
+                     + c_lg2 - lgy2
                      + (((y * y) - (A * A)) / var) * det_log((A * y) / var)
-                     + logy - c.lg[ci];
+                     + logy - c_lg;
     double pch = det_exp(lnp);
     if (X == 0) pch = (y < A) ? 1.0 : 0.0;
     double ub, um;
     us.pair(kAuxBlock, ub, um);
     if (um <= pch) {
-        c.lg1[ci] = lgy1; c.lg2[ci] = lgy2; c.lg[ci] = logy;
+        c_lg1 = lgy1; c_lg2 = lgy2; c_lg = logy;
         return y;
     }
     return A;
@@ -612,6 +612,8 @@ __global__ void __launch_bounds__(32 * kPWarps) p_family(const PParams p)
     if (!mine) return;
     const double corrE = has2 ? tot_s[warp * PER_WARP + lane] : 0.0;
     double P = p.P[e], Ap = p.Ap[e], Bp = p.Bp[e];
+    double lg1 = p.acache.lg1[e], lg2 = p.acache.lg2[e], lg = p.acache.lg[e];
+    bool has6 = false;
     for (int o = 0; o < p.ops.n; ++o) {
         const int op = p.ops.get(o);
         if (op == 2) {
@@ -622,9 +624,11 @@ __global__ void __launch_bounds__(32 * kPWarps) p_family(const PParams p)
         } else if (op == 4) {
             Bp = update_b(p.key, p.sweep, kStBp, (uint32_t)e, Ap, P, p.h.ap, p.h.bp);
         } else if (op == 6) {
-            Ap = update_a(p.key, p.sweep, kStAp, (uint32_t)e, Ap, P, Bp, p.h.lp, p.h.var_ap, p.acache, (size_t)e);
+            Ap = update_a(p.key, p.sweep, kStAp, (uint32_t)e, Ap, P, Bp, p.h.lp, p.h.var_ap, lg1, lg2, lg);
+            has6 = true;
         }
     }
+    if (has6) { p.acache.lg1[e] = lg1; p.acache.lg2[e] = lg2; p.acache.lg[e] = lg; }
     p.P[e] = P; p.Ap[e] = Ap; p.Bp[e] = Bp;
     if (p.Ps_slot) p.Ps_slot[e] = P;
     if (p.Aps_slot) p.Aps_slot[e] = Ap;
@@ -704,34 +708,65 @@ SG_D void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t 
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
+// The state of one element in registers: loaded and stored by the caller (a lane's two elements are neighbours in memory:
+// one 16-byte access per array instead of two 8-byte ones when they are aligned).
+struct EState { double E, Ae, Be, lg1, lg2, lg; int Znj; };
+
 // inlined: the kernel's parameters are read from the constant bank (a call by reference would copy them to the stack,
 // and every p.X inside would be a local-memory load -- 60 % of those missed L1 in the round-1 profile)
-SG_D void e_update_element(const EParams &p, size_t e, double corrP, double &Eo)
+SG_D void e_update_element(const EParams &p, size_t e, double corrP, EState &s)
 {
-    double E = p.E[e], Ae = p.Ae[e], Be = p.Be[e];
     const uint32_t eg = (uint32_t)(e + (size_t)p.K * p.col0);        // global element k + K*j of the streams
     for (int o = 0; o < p.ops.n; ++o) {
         const int op = p.ops.get(o);
         if (op == 3) {
             UStream us; us.init(p.key, p.sweep, kStE, eg);
-            const double shape = Ae + 1 + (double)p.Znj[e];
-            const double rate = Be + corrP;
-            E = gamma_draw(us, shape, rate);
+            const double shape = s.Ae + 1 + (double)s.Znj;
+            const double rate = s.Be + corrP;
+            s.E = gamma_draw(us, shape, rate);
         } else if (op == 5) {
-            Be = update_b(p.key, p.sweep, kStBe, eg, Ae, E, p.h.ae, p.h.be);
+            s.Be = update_b(p.key, p.sweep, kStBe, eg, s.Ae, s.E, p.h.ae, p.h.be);
         } else if (op == 7) {
-            Ae = update_a(p.key, p.sweep, kStAe, eg, Ae, E, Be, p.h.le, p.h.var_ae, p.acache, e);
+            s.Ae = update_a(p.key, p.sweep, kStAe, eg, s.Ae, s.E, s.Be, p.h.le, p.h.var_ae, s.lg1, s.lg2, s.lg);
         }
     }
-    p.E[e] = E; p.Ae[e] = Ae; p.Be[e] = Be;
-    if (p.Es_slot) p.Es_slot[e] = E;
-    if (p.Aes_slot) p.Aes_slot[e] = Ae;
-    if (p.Bes_slot) p.Bes_slot[e] = Be;
-    Eo = E;
+}
+
+// a lane's one or two elements (ea, and eb = ea + 1 when two): load
+SG_D void e_load_pair(const EParams &p, size_t ea, bool two, bool vec, EState &a, EState &b)
+{
+    if (vec) {
+        const double2 vE = *reinterpret_cast<const double2 *>(p.E + ea), vA = *reinterpret_cast<const double2 *>(p.Ae + ea);
+        const double2 vB = *reinterpret_cast<const double2 *>(p.Be + ea);
+        const double2 v1 = *reinterpret_cast<const double2 *>(p.acache.lg1 + ea), v2 = *reinterpret_cast<const double2 *>(p.acache.lg2 + ea);
+        const double2 v3 = *reinterpret_cast<const double2 *>(p.acache.lg + ea);
+        const int2 vz = *reinterpret_cast<const int2 *>(p.Znj + ea);
+        a = EState{vE.x, vA.x, vB.x, v1.x, v2.x, v3.x, vz.x};
+        b = EState{vE.y, vA.y, vB.y, v1.y, v2.y, v3.y, vz.y};
+    } else {
+        a = EState{p.E[ea], p.Ae[ea], p.Be[ea], p.acache.lg1[ea], p.acache.lg2[ea], p.acache.lg[ea], p.Znj[ea]};
+        if (two) b = EState{p.E[ea + 1], p.Ae[ea + 1], p.Be[ea + 1], p.acache.lg1[ea + 1], p.acache.lg2[ea + 1], p.acache.lg[ea + 1], p.Znj[ea + 1]};
+    }
+}
+SG_D void e_store2(double *base, size_t ea, bool two, bool vec, double x, double y)
+{
+    if (vec) *reinterpret_cast<double2 *>(base + ea) = make_double2(x, y);
+    else { base[ea] = x; if (two) base[ea + 1] = y; }
+}
+SG_D void e_store_pair(const EParams &p, size_t ea, bool two, bool vec, bool has7, const EState &a, const EState &b)
+{
+    e_store2(p.E, ea, two, vec, a.E, b.E); e_store2(p.Ae, ea, two, vec, a.Ae, b.Ae); e_store2(p.Be, ea, two, vec, a.Be, b.Be);
+    if (has7) {
+        e_store2(p.acache.lg1, ea, two, vec, a.lg1, b.lg1); e_store2(p.acache.lg2, ea, two, vec, a.lg2, b.lg2);
+        e_store2(p.acache.lg, ea, two, vec, a.lg, b.lg);
+    }
+    if (p.Es_slot) e_store2(p.Es_slot, ea, two, vec, a.E, b.E);
+    if (p.Aes_slot) e_store2(p.Aes_slot, ea, two, vec, a.Ae, b.Ae);
+    if (p.Bes_slot) e_store2(p.Bes_slot, ea, two, vec, a.Be, b.Be);
 }
 
 #ifdef SG_Z_TIMING      // experiments only: per-block phase clocks of the last e_family launch
-__device__ long long g_e_clock[4096][5];
+__device__ long long g_e_clock[4096][8];
 #define SG_ECLK(slot) if (threadIdx.x == 0 && blockIdx.x < 4096) g_e_clock[blockIdx.x][slot] = clock64();
 #else
 #define SG_ECLK(slot)
@@ -762,6 +797,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const _
     __shared__ __align__(8) uint64_t mbar[NS];
     // [NS][kERows][kEPitch]; TMA wants its destination 128-byte aligned (a slot is 204 x 128 bytes)
     double *Ws = reinterpret_cast<double *>(e_smem + ((128u - (smem_u32(e_smem) & 127u)) & 127u));
+    SG_ECLK(0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int I = p.I, J = p.J, K = p.K;
     const int npairs = e_pairs(K), n_tasks = e_groups(J) * npairs;
@@ -783,7 +819,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const _
 #pragma unroll
     for (int s = 0; s < NS; ++s) nload[s] = 0;
     prefetch_tables(tid - 32);
-    SG_ECLK(0)
+    SG_ECLK(5)
 
     // thread 0 sends contexts [r0, r0 + kERows) of column group cg into `slot`: ONE request to the TMA unit (the box is
     // kEPitch = 34 genomes wide, so the tile lands with the padded pitch; a request per 256-byte row, as in the first
@@ -829,10 +865,6 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const _
                 start_stream(cg0);
             }
         }
-        if (jin && p.ops.n) {                               // the element state is wanted after pass 1: start bringing it in
-            sg_prefetch(p.E + ea); sg_prefetch(p.Ae + ea); sg_prefetch(p.Be + ea); sg_prefetch(p.Znj + ea);
-            sg_prefetch(p.acache.lg1 + ea); sg_prefetch(p.acache.lg2 + ea); sg_prefetch(p.acache.lg + ea);
-        }
         // ---- pass 1: corrP = P'W for (ka, kb) x this lane's genome
         double acc0 = 0.0, acc1 = 0.0;
         if (has3) {
@@ -842,35 +874,28 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const _
                 if (active) {
                     const double *Wt = Ws + (size_t)slot * kERows * kEPitch + lane;
                     const double *P0 = p.P + (size_t)I * ka + r0, *P1 = p.P + (size_t)I * kb + r0;
-                    if (MAXW == 8) {                        // I*K*8 bytes of P stay in L1: warp-uniform loads
-                        wait_tile(slot);
-#pragma unroll 8
-                        for (int r = 0; r < rows; ++r) {
-                            const double w = Wt[r * kEPitch];
-                            acc0 = fma(__ldg(P0 + r), w, acc0);
-                            acc1 = fma(__ldg(P1 + r), w, acc1);
-                        }
-                    } else {
-                        // wide context sets: P does not fit L1 next to the tiles.  The chunk's 96 rows of the two classes are
-                        // read coalesced into registers (three rows per lane and class, on their way while the tile
-                        // arrives) and handed round by shuffle
-                        double pa[3], pb[3];
+                    // The chunk's (up to) 96 rows of the two classes' columns of P are read coalesced into registers -- three
+                    // rows per lane and class, on their way while the tile arrives -- and handed round by shuffle.  (Warp-
+                    // uniform loads inside the loop met a cold L1 in every launch: two new lines per eight steps at L2
+                    // latency, 160 cycles per step.)
+                    double pa[3], pb[3];
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const int r = 32 * q + lane;
-                            pa[q] = r < rows ? __ldg(P0 + r) : 0.0;
-                            pb[q] = r < rows ? __ldg(P1 + r) : 0.0;
-                        }
-                        wait_tile(slot);
+                    for (int q = 0; q < 3; ++q) {
+                        const int r = 32 * q + lane;
+                        pa[q] = r < rows ? __ldg(P0 + r) : 0.0;
+                        pb[q] = r < rows ? __ldg(P1 + r) : 0.0;
+                    }
+                    SG_ECLK(6)
+                    wait_tile(slot);
+                    SG_ECLK(7)
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const int nr = min(32, rows - 32 * q);
+                    for (int q = 0; q < 3; ++q) {
+                        const int nr = min(32, rows - 32 * q);
 #pragma unroll 8
-                            for (int l = 0; l < nr; ++l) {
-                                const double w = Wt[(32 * q + l) * kEPitch];
-                                acc0 = fma(__shfl_sync(kFull, pa[q], l), w, acc0);
-                                acc1 = fma(__shfl_sync(kFull, pb[q], l), w, acc1);
-                            }
+                        for (int l = 0; l < nr; ++l) {
+                            const double w = Wt[(32 * q + l) * kEPitch];
+                            acc0 = fma(__shfl_sync(kFull, pa[q], l), w, acc0);
+                            acc1 = fma(__shfl_sync(kFull, pb[q], l), w, acc1);
                         }
                     }
                 }
@@ -882,19 +907,27 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const _
         }
         SG_ECLK(1)
         // ---- the element updates of this sweep, two elements per lane
+        // the lane's element state (E, Ae, Be, sum_i Z, the three cached A terms)
         double Ea = 0.0, Eb = 0.0;
         if (jin) {
+            EState sa{}, sb{};
+            // neighbours, and 16-byte aligned in every array (the A-term caches and the sample slots are laid out K*J doubles
+            // apart, so K*J must be even as well; always the case when K is even)
+            const bool vec = has_b && ((ea & 1) == 0) && ((((size_t)K * J) & 1) == 0);
+            e_load_pair(p, ea, has_b, vec, sa, sb);
             if (p.ops.n) {
+                bool has7 = false;
+                for (int o = 0; o < p.ops.n; ++o) has7 |= (p.ops.get(o) == 7);
 #pragma unroll 1
                 for (int el = 0; el < (has_b ? 2 : 1); ++el) {          // one copy of the inlined update code
-                    double Eo;
-                    e_update_element(p, el ? eb : ea, el ? acc1 : acc0, Eo);
-                    if (el) Eb = Eo; else Ea = Eo;
+                    EState s = el ? sb : sa;
+                    e_update_element(p, el ? eb : ea, el ? acc1 : acc0, s);
+                    if (el) sb = s; else sa = s;
                 }
-            } else {
-                Ea = p.E[ea];
-                if (has_b) Eb = p.E[eb];
+                e_store_pair(p, ea, has_b, vec, has7, sa, sb);
             }
+            Ea = sa.E;
+            if (has_b) Eb = sb.E;
         }
         SG_ECLK(2)
         if (!p.do_corrE) { base = end; continue; }

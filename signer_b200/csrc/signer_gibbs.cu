@@ -1463,7 +1463,7 @@ void signer_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 #ifdef SG_Z_TIMING
 extern "C" int signer_debug_e_clocks(long long *out, int nblocks)
 {
-    return (int)cudaMemcpyFromSymbol(out, sg::g_e_clock, sizeof(long long) * 5 * (size_t)nblocks);
+    return (int)cudaMemcpyFromSymbol(out, sg::g_e_clock, sizeof(long long) * 8 * (size_t)nblocks);
 }
 extern "C" int signer_debug_z_phases(unsigned long long *out)
 {
