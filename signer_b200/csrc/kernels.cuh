@@ -687,7 +687,8 @@ constexpr int kERows = 96;        // contexts per staged chunk of W
 constexpr int kEPitch = 34;       // doubles per staged row: 272 B keeps every row 16-byte aligned for the bulk copies; lanes
                                   // that walk down a column (pass 2) meet two-way bank conflicts only
 __host__ __device__ constexpr int e_slots(int maxw) { return maxw == 8 ? 2 : 4; }
-inline size_t e_smem_bytes(int maxw) { return sizeof(double) * e_slots(maxw) * kERows * kEPitch + 128; }
+// the tile slots, a strip of 2 x kERows doubles per warp for the two classes' rows of P, slack for the 128-byte alignment
+inline size_t e_smem_bytes(int maxw) { return sizeof(double) * ((size_t)e_slots(maxw) * kERows * kEPitch + (size_t)maxw * 2 * kERows) + 128; }
 
 SG_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 SG_D void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -874,29 +875,29 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const _
                 if (active) {
                     const double *Wt = Ws + (size_t)slot * kERows * kEPitch + lane;
                     const double *P0 = p.P + (size_t)I * ka + r0, *P1 = p.P + (size_t)I * kb + r0;
-                    // The chunk's (up to) 96 rows of the two classes' columns of P are read coalesced into registers -- three
-                    // rows per lane and class, on their way while the tile arrives -- and handed round by shuffle.  (Warp-
-                    // uniform loads inside the loop met a cold L1 in every launch: two new lines per eight steps at L2
-                    // latency, 160 cycles per step.)
-                    double pa[3], pb[3];
+                    // The chunk's (up to) 96 rows of the two classes' columns of P: read coalesced (three rows per lane and
+                    // class, on their way while the tile arrives) into the warp's own strip of shared memory, interleaved, so
+                    // that a step of the chain is one broadcast 16-byte load for both classes next to the lane's W value.
+                    // (Warp-uniform global loads inside the loop met a cold L1 in every launch -- two new lines per eight steps
+                    // at L2 latency, 160 cycles per step; handing the values round by shuffle was bound by shuffle throughput,
+                    // 96 shuffles per step and SM, 130 cycles per step.)
+                    double *Pw = Ws + (size_t)NS * kERows * kEPitch + (size_t)warp * 2 * kERows;
+                    __syncwarp();                           // the strip's previous chunk has been consumed by every lane
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         const int r = 32 * q + lane;
-                        pa[q] = r < rows ? __ldg(P0 + r) : 0.0;
-                        pb[q] = r < rows ? __ldg(P1 + r) : 0.0;
+                        if (r < rows) *reinterpret_cast<double2 *>(Pw + 2 * r) = make_double2(__ldg(P0 + r), __ldg(P1 + r));
                     }
+                    __syncwarp();
                     SG_ECLK(6)
                     wait_tile(slot);
                     SG_ECLK(7)
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int nr = min(32, rows - 32 * q);
 #pragma unroll 8
-                        for (int l = 0; l < nr; ++l) {
-                            const double w = Wt[(32 * q + l) * kEPitch];
-                            acc0 = fma(__shfl_sync(kFull, pa[q], l), w, acc0);
-                            acc1 = fma(__shfl_sync(kFull, pb[q], l), w, acc1);
-                        }
+                    for (int r = 0; r < rows; ++r) {
+                        const double w = Wt[r * kEPitch];
+                        const double2 pp = *reinterpret_cast<const double2 *>(Pw + 2 * r);
+                        acc0 = fma(pp.x, w, acc0);
+                        acc1 = fma(pp.y, w, acc1);
                     }
                 }
                 if (nchunks > 1) {
