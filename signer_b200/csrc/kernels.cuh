@@ -999,7 +999,7 @@ constexpr int kLLRound = 96;      // rows per round: three chunks; every warp ev
 // 32 genomes per block, lanes = genomes.  A round covers 96 rows: warp w evaluates the terms of rows 12w .. 12w+11
 // (four rows in flight: four independent fma chains over k) into shared memory; then the first three warps add the
 // terms of one chunk each in row order, and the first warp adds the chunk sums to the genome's total in chunk order.
-inline size_t loglik_smem_bytes(int K) { return sizeof(double) * ((size_t)K * 33 + (size_t)kLLRound * 33 + 3 * 32); }
+inline size_t loglik_smem_bytes(int K) { return sizeof(double) * ((size_t)K * 33 + (size_t)kLLRound * 33 + 3 * 32 + (size_t)K * kLLRound); }
 
 __global__ void __launch_bounds__(32 * kLLWarps, 3) loglik_cols(const LLParams p)
 {
@@ -1008,6 +1008,8 @@ __global__ void __launch_bounds__(32 * kLLWarps, 3) loglik_cols(const LLParams p
     double *E_s = reinterpret_cast<double *>(smem_raw);   // [K][33]
     double *term = E_s + K * 33;                          // [kLLRound][33]
     double *csum = term + kLLRound * 33;                  // [3][32]
+    double *P_s = csum + 3 * 32;                          // [K][kLLRound]: this round's rows of P (warp-uniform global loads in
+                                                          // the k loop met a cold L1 in every launch: one L2 round trip per class)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int j0 = blockIdx.x * 32, j = j0 + lane, jc = min(j, J - 1);
     if (p.mode == 0) {
@@ -1018,7 +1020,15 @@ __global__ void __launch_bounds__(32 * kLLWarps, 3) loglik_cols(const LLParams p
     }
     double a = 0.0;
     for (int i0 = 0; i0 < I; i0 += kLLRound) {
-        __syncthreads();                                  // E_s staged; term / csum of the previous round consumed
+        if (p.mode == 0) {
+            if (i0) __syncthreads();                      // the previous round's rows of P have been used
+            const int rows = min(kLLRound, I - i0);
+            for (int idx = tid; idx < K * rows; idx += 32 * kLLWarps) {
+                const int kk = idx / rows, r = idx - kk * rows;
+                P_s[kk * kLLRound + r] = p.P[(size_t)I * kk + i0 + r];
+            }
+        }
+        __syncthreads();                                  // E_s, P_s staged; term / csum of the previous round consumed
         for (int g = 0; g < 3; ++g) {
             const int rb = 12 * w + 4 * g, ib = i0 + rb;  // four rows ib .. ib+3 (clamped; rows beyond I are not added)
             if (ib >= I) break;
@@ -1030,16 +1040,12 @@ __global__ void __launch_bounds__(32 * kLLWarps, 3) loglik_cols(const LLParams p
                 const double wa = p.W[(size_t)ia * p.Jp + jc], wb = p.W[(size_t)ib1 * p.Jp + jc];
                 const double wc = p.W[(size_t)ic * p.Jp + jc], wd = p.W[(size_t)id * p.Jp + jc];
                 double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
-                const double *Pk = p.P;
-                double qa = __ldg(Pk + ia), qb = __ldg(Pk + ib1), qc = __ldg(Pk + ic), qd = __ldg(Pk + id);
-                for (int k = 0; k < K; ++k) {                                 // the next class's P values load while this one's fmas run
+                const double *Pa = P_s + (ia - i0), *Pb = P_s + (ib1 - i0), *Pc = P_s + (ic - i0), *Pd = P_s + (id - i0);
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {                                 // four rows' chains side by side; P by broadcast from shared memory
                     const double e = E_s[k * 33 + lane];
-                    const double ra = qa, rb2 = qb, rc = qc, rd = qd;
-                    if (k + 1 < K) {
-                        Pk += I;
-                        qa = __ldg(Pk + ia); qb = __ldg(Pk + ib1); qc = __ldg(Pk + ic); qd = __ldg(Pk + id);
-                    }
-                    pa = fma(ra, e, pa); pb = fma(rb2, e, pb); pc = fma(rc, e, pc); pd = fma(rd, e, pd);
+                    pa = fma(Pa[k * kLLRound], e, pa); pb = fma(Pb[k * kLLRound], e, pb);
+                    pc = fma(Pc[k * kLLRound], e, pc); pd = fma(Pd[k * kLLRound], e, pd);
                 }
                 const double la = pa * wa, lb = pb * wb, lc = pc * wc, ld = pd * wd;
                 ta = ma * det_log(la) - la; tb = mb * det_log(lb) - lb;

@@ -60,7 +60,7 @@ int ensure_device_setup(int device)
     CU(cudaFuncGetAttributes(&fa, z_alloc_fused));
     g_z_dyn_smem_max[device] = optin - (int)fa.sharedSizeBytes;
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
-    CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (33 K + 3264) bytes: above 48 KB from K = 88 (K <= 128 is accepted)
+    CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (129 K + 3264) bytes: above 48 KB from K = 23; 158 KB at K = 128, the largest accepted
     CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, e_family<kEWarps>));    // two W tiles: 51 KB
     CU(cudaFuncSetAttribute(e_family<kEWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
@@ -460,7 +460,9 @@ int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slo
     return SIGNER_OK;
 }
 
-int ensure_rings(signer_chain *c, int eval, int keep_par)
+// Sweeps per ring chunk: what fits a ring set, but at least four chunks per run, so that also a short run (the EM loop's
+// 100 evaluation sweeps, the 10 of a smoke-sized call) sends most of its samples home while it is still sweeping
+int ring_chunk(const signer_chain *c, int eval, int keep_par)
 {
     const size_t per_sweep = sizeof(double) * (c->nP + c->nE) * (keep_par ? 3 : 2);
     size_t ring_bytes = kRingBytes;
@@ -468,7 +470,13 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
         const long long v = std::atoll(e);
         if (v > 0) ring_bytes = (size_t)v;
     }
-    int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes / per_sweep));
+    const size_t fit = std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes / per_sweep));
+    return (int)std::max<size_t>(1, std::min<size_t>(fit, ((size_t)eval + 3) / 4));
+}
+
+int ensure_rings(signer_chain *c, int eval, int keep_par)
+{
+    const int cap = ring_chunk(c, eval, keep_par);
     if (c->ring_cap >= cap && c->ring_keep >= keep_par) return SIGNER_OK;
     for (int b = 0; b < 2; ++b) {
         signer_chain::free_ring(c->ring[b], c->stream);
@@ -749,7 +757,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         c->stats_valid = false;
         if (do_stats) CU(cudaMemsetAsync(c->stats, 0, 8 * sizeof(double), c->stream));
     }
-    const int total = burn + eval, cap = std::max(1, want_rings ? c->ring_cap : eval);
+    const int total = burn + eval, cap = std::max(1, want_rings ? ring_chunk(c, eval, keep_par) : eval);
     int chunk_r0 = 0;
     std::vector<std::thread> faulters;
     auto join_faulters = [&]() { for (auto &t : faulters) if (t.joinable()) t.join(); faulters.clear(); };
