@@ -1,7 +1,7 @@
 """The reference-shaped stateless call at the driver's bench size (burn = eval = 10) and the EM-shaped call
 (burn 200 + eval 100, keep_par), with the library's phase trace (SIGNER_TRACE=1).  Run on the GPU box."""
 import os, sys, time
-os.environ["SIGNER_TRACE"] = "1"
+os.environ.setdefault("SIGNER_TRACE", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import signer_b200 as sg

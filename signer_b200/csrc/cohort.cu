@@ -200,8 +200,7 @@ int get_cohort(int device, int I, int J, const double *M, const double *W, int c
     if (limit == 0) return build_cohort(device, I, J, M, W, col0, Jglobal, out);
     CacheKey key{device, I, J, col0, Jglobal, {0, 0}, {0, 0}};
     const size_t bytes = (size_t)I * J * sizeof(double);
-    hash128(M, bytes, key.hm);
-    hash128(W, bytes, key.hw);
+    hash128_two(M, W, bytes, key.hm, key.hw);
     std::lock_guard<std::mutex> lk(g_cache_mu);        // builds are serialised: a second caller with the same content waits and hits
     for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
         if (it->first == key) {

@@ -225,18 +225,19 @@ void hash_chunk(const unsigned char *p, size_t bytes, uint64_t seed, uint64_t ou
 }
 }
 
-void hash128(const void *p, size_t bytes, uint64_t out[2])
+void hash128_two(const void *pa, const void *pb, size_t bytes, uint64_t ha[2], uint64_t hb[2])
 {
-    const unsigned char *b = static_cast<const unsigned char *>(p);
-    const size_t kChunk = size_t(4) << 20;
+    const unsigned char *b[2] = {static_cast<const unsigned char *>(pa), static_cast<const unsigned char *>(pb)};
+    const int nbuf = pb ? 2 : 1;
+    const size_t kChunk = size_t(512) << 10;             // small enough that 2 x 7.7 MB keep eight threads busy
     const size_t nchunks = std::max<size_t>(1, (bytes + kChunk - 1) / kChunk);
-    std::vector<uint64_t> h(2 * nchunks);
+    std::vector<uint64_t> h(2 * nchunks * nbuf);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nth = std::min<size_t>({nchunks, (size_t)8, (size_t)hw});
+    const size_t nth = std::min<size_t>({nchunks * nbuf, (size_t)8, (size_t)hw});
     auto work = [&](size_t t) {
-        for (size_t c = t; c < nchunks; c += nth) {
-            const size_t off = c * kChunk;
-            hash_chunk(b + off, std::min(kChunk, bytes - off), (uint64_t)c, &h[2 * c]);
+        for (size_t c = t; c < nchunks * nbuf; c += nth) {
+            const size_t which = c / nchunks, cc = c - which * nchunks, off = cc * kChunk;
+            hash_chunk(b[which] + off, std::min(kChunk, bytes - std::min(bytes, off)), (uint64_t)cc, &h[2 * c]);
         }
     };
     if (nth <= 1) work(0);
@@ -246,7 +247,10 @@ void hash128(const void *p, size_t bytes, uint64_t out[2])
         work(0);
         for (auto &x : th) x.join();
     }
-    hash_chunk(reinterpret_cast<const unsigned char *>(h.data()), h.size() * 8, (uint64_t)bytes, out);
+    hash_chunk(reinterpret_cast<const unsigned char *>(h.data()), nchunks * 16, (uint64_t)bytes, ha);
+    if (pb) hash_chunk(reinterpret_cast<const unsigned char *>(h.data() + 2 * nchunks), nchunks * 16, (uint64_t)bytes, hb);
 }
+
+void hash128(const void *p, size_t bytes, uint64_t out[2]) { hash128_two(p, nullptr, bytes, out, nullptr); }
 
 } // namespace sgh

@@ -161,5 +161,7 @@ void prefault(void *p, size_t bytes);
 
 // 128-bit content hash of a host array (cohort cache key), multi-threaded for large arrays
 void hash128(const void *p, size_t bytes, uint64_t out[2]);
+// the same for two buffers of equal length in one fan-out of threads (M and W of a cohort)
+void hash128_two(const void *a, const void *b, size_t bytes, uint64_t ha[2], uint64_t hb[2]);
 
 } // namespace sgh

@@ -39,7 +39,7 @@ namespace {
 
 thread_local double g_loop_ms = 0.0;      // wall time of the last sweep loop on this thread (sharded / stateless runs)
 
-constexpr size_t kRingBytes = size_t(256) << 20;   // per ring set (two sets): small enough to pipeline D2H behind compute
+constexpr size_t kRingBytes = size_t(64) << 20;    // per ring set (two sets): what is still on the device when the last sweep ends is the call's tail
 
 // z_alloc_fused and loglik_cols may need more than 48 KB of dynamic shared memory; raise the limits once per device to
 // the architectural maximum so that concurrent chains with different K never race on the attribute.
@@ -460,7 +460,7 @@ int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slo
     return SIGNER_OK;
 }
 
-// Sweeps per ring chunk: what fits a ring set, but at least four chunks per run, so that also a short run (the EM loop's
+// Sweeps per ring chunk: what fits a ring set, but at least eight chunks per run, so that also a short run (the EM loop's
 // 100 evaluation sweeps, the 10 of a smoke-sized call) sends most of its samples home while it is still sweeping
 int ring_chunk(const signer_chain *c, int eval, int keep_par)
 {
@@ -471,7 +471,7 @@ int ring_chunk(const signer_chain *c, int eval, int keep_par)
         if (v > 0) ring_bytes = (size_t)v;
     }
     const size_t fit = std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes / per_sweep));
-    return (int)std::max<size_t>(1, std::min<size_t>(fit, ((size_t)eval + 3) / 4));
+    return (int)std::max<size_t>(1, std::min<size_t>(fit, ((size_t)eval + 7) / 8));
 }
 
 int ensure_rings(signer_chain *c, int eval, int keep_par)
@@ -558,7 +558,8 @@ int device_summaries(signer_chain *c, int R, double *Phat, double *Ehat)
 }
 
 // the six state matrices come back with one copy of the state block through the chain's pinned buffer
-int fetch_state(signer_chain *c, signer_outputs *out)
+// (two halves, so that a run can put the copy on the stream behind its last sweep and collect it after its samples have left)
+int fetch_state_begin(signer_chain *c, const signer_outputs *out)
 {
     CU(cudaSetDevice(c->device));
     const bool any_state = out->P || out->Ap || out->Bp || out->E || out->Ae || out->Be;
@@ -570,6 +571,14 @@ int fetch_state(signer_chain *c, signer_outputs *out)
     if (any_state) CU(cudaMemcpyAsync(hs, c->state_block, sd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (out->Zin) CU(cudaMemcpyAsync(hz, c->Zin[c->zcur], c->nP * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (out->Znj) CU(cudaMemcpyAsync(hz + c->nP, c->Znj[c->zcur], c->nE * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return SIGNER_OK;
+}
+
+int fetch_state_end(signer_chain *c, signer_outputs *out)
+{
+    const size_t sd = 3 * (c->nPp + c->nEp);
+    const double *hs = c->hstate.as<double>();
+    const int *hz = reinterpret_cast<const int *>(hs + sd);
     CU(cudaStreamSynchronize(c->stream));
     auto cp = [&](double *dst, size_t off, size_t n) { if (dst) std::memcpy(dst, hs + off, n * sizeof(double)); };
     cp(out->P, 0, c->nP); cp(out->Ap, c->nPp, c->nP); cp(out->Bp, 2 * c->nPp, c->nP);
@@ -577,6 +586,12 @@ int fetch_state(signer_chain *c, signer_outputs *out)
     if (out->Zin) std::memcpy(out->Zin, hz, c->nP * sizeof(int));
     if (out->Znj) std::memcpy(out->Znj, hz + c->nP, c->nE * sizeof(int));
     return SIGNER_OK;
+}
+
+int fetch_state(signer_chain *c, signer_outputs *out)
+{
+    ST(fetch_state_begin(c, out));
+    return fetch_state_end(c, out);
 }
 
 // Reduce the given I x J x K cube (pageable host memory; columns [c0, c0+Jl) of every slice) to the chain's
@@ -729,6 +744,10 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     if (burn < 0 || eval < 0) return fail(SIGNER_ERR_ARG, "burn and eval must be non-negative");
     CU(cudaSetDevice(c->device));
     keep_par = keep_par ? 1 : 0;
+    static const bool trace = [] { const char *e = std::getenv("SIGNER_TRACE"); return e && e[0] == '2'; }();   // SIGNER_TRACE=2: phases of this function
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    double tr[6] = {0, 0, 0, 0, 0, 0};
     // Sample rings: needed when samples leave for the host, and for a run that keeps everything on the device (out == NULL:
     // the EM loop reads their statistics).  A caller that asks only for log-likelihoods / BICs (the model-selection path,
     // signer_gibbs_batch) gets no ring stores at all.
@@ -786,6 +805,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     GroupPtr cube_group = sgh::make_group();
     Joiner drain_cube{[c, &cube_group]() { TransferPool::of(c->device).wait(cube_group); }};
     const auto t_enqueue = std::chrono::steady_clock::now();
+    tr[0] = since();
     for (int k = 0; k < total; ++k) {
         const uint32_t sweep = c->sweep0 + (uint32_t)c->sweeps_done;
         int order[7];
@@ -824,9 +844,11 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         c->sweeps_done++;
     }
     ST(wait_loglik(c));                                    // the launching stream ends after the last log-likelihood
+    tr[1] = since();
     c->last_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enqueue).count();
     c->last_eval = eval;
     if (eval > 0 && do_stats) { c->stats_valid = true; c->stats_np = (double)c->nP * eval; c->stats_ne = (double)c->nE * eval; }
+    if (out) ST(fetch_state_begin(c, out));                // behind the last sweep on the stream; collected below
     if (out && eval > 0) {
         if (zcube && out->Zs) {
             // step 1 may not have run in the last sweep only under a forced order; then Zs is undefined.  The cube leaves
@@ -840,9 +862,12 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
                                   sizeof(double) * (size_t)c->I * c->J, c->cube_done, cube_group);
         }
         CU(cudaStreamSynchronize(c->stream));
+        tr[2] = since();
         if (want_rings) { ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1])); }
         ST(wait_group(c->device, cube_group, "copy-out of the Z cube"));
+        tr[3] = since();
         join_faulters();
+        tr[4] = since();
         if (summ) {
             if (out->Ps) CU(cudaMemcpy(out->Ps, c->sumPs, sizeof(double) * c->nP * (size_t)eval, cudaMemcpyDeviceToHost));
             if (out->Es) CU(cudaMemcpy(out->Es, c->sumEs, sizeof(double) * c->nE * (size_t)eval, cudaMemcpyDeviceToHost));
@@ -860,7 +885,11 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             }
         }
     }
-    if (out) ST(fetch_state(c, out));
+    if (out) ST(fetch_state_end(c, out));
+    tr[5] = since();
+    if (trace)
+        std::fprintf(stderr, "[chain_run] set-up %.2f ms, enqueue %.2f, device done +%.2f, copy-out drained +%.2f, page touchers joined +%.2f, "
+                     "log-likelihoods + state back +%.2f (total %.2f ms)\n", tr[0], tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[5]);
     return SIGNER_OK;
 }
 
@@ -1303,7 +1332,7 @@ int signer_gibbs_run(const signer_problem *pr, const signer_state *st, const sig
 {
     g_err.clear();
     if (!pr || !st || !o || !out) return fail(SIGNER_ERR_ARG, "null argument");
-    static const bool trace = [] { const char *e = std::getenv("SIGNER_TRACE"); return e && e[0] == '1'; }();   // phase times on stderr
+    static const bool trace = [] { const char *e = std::getenv("SIGNER_TRACE"); return e && (e[0] == '1' || e[0] == '2'); }();   // phase times on stderr
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     std::shared_ptr<DeviceData> d;
