@@ -39,6 +39,7 @@ namespace {
 
 thread_local double g_loop_ms = 0.0;      // wall time of the last sweep loop on this thread (sharded / stateless runs)
 
+constexpr int kMaxRingSets = 8;                     // short runs: one set per chunk, the host never waits for a set to drain
 constexpr size_t kRingBytes = size_t(64) << 20;    // per ring set (two sets): what is still on the device when the last sweep ends is the call's tail
 
 // z_alloc_fused and loglik_cols may need more than 48 KB of dynamic shared memory; raise the limits once per device to
@@ -200,8 +201,8 @@ struct signer_chain {
     cudaStream_t ll_stream = nullptr;
     cudaEvent_t ll_ready = nullptr, ll_done = nullptr, cube_done = nullptr;
     bool ll_pending = false;
-    Ring ring[2];
-    int ring_cap = 0, ring_keep = 0;
+    Ring ring[kMaxRingSets];
+    int ring_cap = 0, ring_keep = 0, ring_sets = 0;
     int last_eval = 0;
     double last_enqueue_ms = 0.0;            // host time the last run spent enqueuing its sweeps (before waiting for the device)
     bool profiling = false;
@@ -217,10 +218,8 @@ struct signer_chain {
         for (void *p : {(void *)state_block, (void *)corrE_part, (void *)corrE_all, (void *)col, (void *)ll_ring, (void *)Zcube, (void *)stats,
                         (void *)sumPs, (void *)sumEs, (void *)acache_p, (void *)acache_e, (void *)tile_counter, (void *)draw_count, (void *)ll_ticket})
             dfree(p, fs);
-        for (int b = 0; b < 2; ++b) {
-            dfree(Zin[b], fs); dfree(Znj[b], fs);
-            free_ring(ring[b], fs);
-        }
+        for (int b = 0; b < 2; ++b) { dfree(Zin[b], fs); dfree(Znj[b], fs); }
+        for (int b = 0; b < kMaxRingSets; ++b) free_ring(ring[b], fs);
         for (auto &v : ev) for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream) { cudaStreamSynchronize(own_stream); cudaStreamDestroy(own_stream); }
         if (ll_stream) cudaStreamDestroy(ll_stream);
@@ -462,24 +461,37 @@ int enqueue_sweep(signer_chain *c, uint32_t sweep, const int order[7], const Slo
 
 // Sweeps per ring chunk: what fits a ring set, but at least eight chunks per run, so that also a short run (the EM loop's
 // 100 evaluation sweeps, the 10 of a smoke-sized call) sends most of its samples home while it is still sweeping
+size_t ring_bytes_limit()
+{
+    if (const char *e = std::getenv("SIGNER_RING_BYTES")) {     // tests: force many small chunks through the copy-out path
+        const long long v = std::atoll(e);
+        if (v > 0) return (size_t)v;
+    }
+    return kRingBytes;
+}
+
 int ring_chunk(const signer_chain *c, int eval, int keep_par)
 {
     const size_t per_sweep = sizeof(double) * (c->nP + c->nE) * (keep_par ? 3 : 2);
-    size_t ring_bytes = kRingBytes;
-    if (const char *e = std::getenv("SIGNER_RING_BYTES")) {     // tests: force many small chunks through the copy-out path
-        const long long v = std::atoll(e);
-        if (v > 0) ring_bytes = (size_t)v;
-    }
-    const size_t fit = std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes / per_sweep));
+    const size_t fit = std::max<size_t>(1, std::min<size_t>((size_t)eval, ring_bytes_limit() / per_sweep));
     return (int)std::max<size_t>(1, std::min<size_t>(fit, ((size_t)eval + 7) / 8));
+}
+
+// Ring sets: two of up to kRingBytes each, or more (smaller) ones within the same memory when the chunks are short
+int ring_set_count(const signer_chain *c, int eval, int keep_par)
+{
+    const size_t per_sweep = sizeof(double) * (c->nP + c->nE) * (keep_par ? 3 : 2);
+    const int cap = ring_chunk(c, eval, keep_par), chunks = (eval + cap - 1) / cap;
+    const size_t fit = (2 * ring_bytes_limit()) / std::max<size_t>(1, per_sweep * (size_t)cap);
+    return (int)std::max<size_t>(2, std::min<size_t>({(size_t)kMaxRingSets, fit, (size_t)chunks}));
 }
 
 int ensure_rings(signer_chain *c, int eval, int keep_par)
 {
-    const int cap = ring_chunk(c, eval, keep_par);
-    if (c->ring_cap >= cap && c->ring_keep >= keep_par) return SIGNER_OK;
-    for (int b = 0; b < 2; ++b) {
-        signer_chain::free_ring(c->ring[b], c->stream);
+    const int cap = ring_chunk(c, eval, keep_par), sets = ring_set_count(c, eval, keep_par);
+    if (c->ring_cap >= cap && c->ring_keep >= keep_par && c->ring_sets >= sets) return SIGNER_OK;
+    for (int b = 0; b < kMaxRingSets; ++b) signer_chain::free_ring(c->ring[b], c->stream);
+    for (int b = 0; b < sets; ++b) {
         Ring &r = c->ring[b];
         ST(dalloc(&r.Ps, c->nP * cap, c->stream));
         ST(dalloc(&r.Es, c->nE * cap, c->stream));
@@ -491,7 +503,7 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
         }
         CU(cudaEventCreateWithFlags(&r.filled, cudaEventDisableTiming));
     }
-    c->ring_cap = cap; c->ring_keep = keep_par;
+    c->ring_cap = cap; c->ring_keep = keep_par; c->ring_sets = sets;
     return SIGNER_OK;
 }
 
@@ -499,7 +511,7 @@ int ensure_rings(signer_chain *c, int eval, int keep_par)
 // device's transfer pool, which waits for the ring set's `filled` event
 int flush_chunk(signer_chain *c, int chunk, int r0, int cnt, int keep_par, signer_outputs *out)
 {
-    Ring &r = c->ring[chunk & 1];
+    Ring &r = c->ring[chunk % c->ring_sets];
     TransferPool &pool = TransferPool::of(c->device);
     auto cp = [&](double *dst, const double *src, size_t per) {
         if (!dst || !src) return;
@@ -801,7 +813,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
     }
     struct Joiner { std::function<void()> f; ~Joiner() { f(); } } joiner{join_faulters};
     // whatever way this call ends, no copy-out job may outlive it: they write into the caller's arrays
-    Joiner drain{[c, out]() { if (out) { TransferPool &p = TransferPool::of(c->device); p.wait(c->ring[0].inflight); p.wait(c->ring[1].inflight); } }};
+    Joiner drain{[c, out]() { if (out) { TransferPool &p = TransferPool::of(c->device); for (int b = 0; b < kMaxRingSets; ++b) p.wait(c->ring[b].inflight); } }};
     GroupPtr cube_group = sgh::make_group();
     Joiner drain_cube{[c, &cube_group]() { TransferPool::of(c->device).wait(cube_group); }};
     const auto t_enqueue = std::chrono::steady_clock::now();
@@ -816,10 +828,10 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
             ST(enqueue_sweep(c, sweep, order, nullptr, nullptr));
         } else {
             const int r = k - burn, chunk = r / cap, slot = r % cap;
-            Ring &rg = c->ring[chunk & 1];
+            Ring &rg = c->ring[want_rings ? chunk % c->ring_sets : 0];
             Slots s;
             if (want_rings) {
-                if (slot == 0 && chunk >= 2 && out) ST(wait_ring(c, rg));      // the set's previous chunk has left the device
+                if (slot == 0 && chunk >= c->ring_sets && out) ST(wait_ring(c, rg));      // the set's previous chunk has left the device
                 s.Ps = rg.Ps + c->nP * slot; s.Es = rg.Es + c->nE * slot;
                 s.Bps = rg.Bps + c->nP * slot; s.Bes = rg.Bes + c->nE * slot;
                 if (keep_par) { s.Aps = rg.Aps + c->nP * slot; s.Aes = rg.Aes + c->nE * slot; }
@@ -863,7 +875,7 @@ int chain_run(signer_chain *c, int burn, int eval, int keep_par, const int32_t *
         }
         CU(cudaStreamSynchronize(c->stream));
         tr[2] = since();
-        if (want_rings) { ST(wait_ring(c, c->ring[0])); ST(wait_ring(c, c->ring[1])); }
+        if (want_rings) for (int b = 0; b < c->ring_sets; ++b) ST(wait_ring(c, c->ring[b]));
         ST(wait_group(c->device, cube_group, "copy-out of the Z cube"));
         tr[3] = since();
         join_faulters();
