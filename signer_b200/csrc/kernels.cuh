@@ -790,8 +790,12 @@ inline int e_block_warps(int I, int K)
 // launched with 32 * e_block_warps(I, K) threads.  MAXW = 8: contexts fit one tile (three blocks per SM); MAXW = 16: the
 // contexts stream through in chunks, and one block takes ALL class pairs of a column group in one round (up to 16
 // warps), so that the tile is streamed once per pass instead of once per pass and round
-template <int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1) e_family(const __grid_constant__ EParams p)
+// MINB: resident blocks per SM the register budget is set for.  The narrow kernel comes in two budgets: 3 blocks (80
+// registers, 24 warps per SM: config 3 at K = 19, 20 needs that many warp slots to stay in one round) and 2 blocks (128
+// registers, nothing spilled: a task takes ~42 us instead of ~64 when the chain's tasks fit 16 warps per SM or need
+// several rounds anyway); chain_create picks by the estimated rounds x round time.
+template <int MAXW, int MINB>
+__global__ void __launch_bounds__(32 * MAXW, MINB) e_family(const __grid_constant__ EParams p)
 {
     constexpr int NS = e_slots(MAXW);                       // tile slots: two column groups, or a ring of context chunks
     extern __shared__ __align__(128) unsigned char e_smem[];

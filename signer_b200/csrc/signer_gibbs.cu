@@ -63,10 +63,12 @@ int ensure_device_setup(int device)
     CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
     CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (129 K + 3264) bytes: above 48 KB from K = 23; 158 KB at K = 128, the largest accepted
     CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-    CU(cudaFuncGetAttributes(&fa, e_family<kEWarps>));    // two W tiles: 51 KB
-    CU(cudaFuncSetAttribute(e_family<kEWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-    CU(cudaFuncGetAttributes(&fa, e_family<kEWarpsWide>));
-    CU(cudaFuncSetAttribute(e_family<kEWarpsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, e_family<kEWarps, 3>));    // two W tiles: 51 KB
+    CU(cudaFuncSetAttribute(e_family<kEWarps, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, e_family<kEWarps, 2>));
+    CU(cudaFuncSetAttribute(e_family<kEWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    CU(cudaFuncGetAttributes(&fa, e_family<kEWarpsWide, 1>));
+    CU(cudaFuncSetAttribute(e_family<kEWarpsWide, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, p_family<2>));          // scratch of the ordered W E' sums grows with the number of genomes
     CU(cudaFuncSetAttribute(p_family<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, p_family<32>));
@@ -187,7 +189,7 @@ struct signer_chain {
     unsigned *ll_ticket = nullptr;               // block counter of loglik_cols' fused tree
     unsigned long long z_launches = 0;
     int z_grid = 0, z_warps = 8, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
-    int e_grid = 1, e_warps = kEWarps, sms = 1;
+    int e_grid = 1, e_warps = kEWarps, e_minb = 3, sms = 1;
     Hyper h{};
     Key key{};
     uint32_t sweep0 = 0;
@@ -346,8 +348,9 @@ int launch_e(signer_chain *c, uint32_t sweep, const Ops &ops, int do_corrE, doub
     ST(wait_loglik(c));
     {
         ProfScope ps(c, 2);
-        if (c->I > kERows) e_family<kEWarpsWide><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarpsWide), c->stream>>>(p);
-        else e_family<kEWarps><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarps), c->stream>>>(p);
+        if (c->I > kERows) e_family<kEWarpsWide, 1><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarpsWide), c->stream>>>(p);
+        else if (c->e_minb == 2) e_family<kEWarps, 2><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarps), c->stream>>>(p);
+        else e_family<kEWarps, 3><<<c->e_grid, 32 * c->e_warps, e_smem_bytes(kEWarps), c->stream>>>(p);
     }
     c->launches++;
     ST(check_launch(c->stream, "e_family"));
@@ -724,9 +727,19 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     c->e_warps = e_block_warps(c->I, K);
     {
         int per_sm = 0;                                   // resident blocks of this width (two 26 KB tiles each)
-        if (c->I > kERows) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family<kEWarpsWide>, 32 * c->e_warps, e_smem_bytes(kEWarpsWide)));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family<kEWarps>, 32 * c->e_warps, e_smem_bytes(kEWarps)));
         const int n_tasks = e_groups(c->J) * e_pairs(K);
+        if (c->I > kERows) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_family<kEWarpsWide, 1>, 32 * c->e_warps, e_smem_bytes(kEWarpsWide)));
+        else {
+            // the register budget: rounds needed x the time of a full round, measured on config 3 (profiles/r02_measurements.md)
+            int per3 = 0, per2 = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, e_family<kEWarps, 3>, 32 * c->e_warps, e_smem_bytes(kEWarps)));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, e_family<kEWarps, 2>, 32 * c->e_warps, e_smem_bytes(kEWarps)));
+            const long long cap3 = (long long)std::max(1, per3) * sms * c->e_warps, cap2 = (long long)std::max(1, per2) * sms * c->e_warps;
+            const double est3 = (double)((n_tasks + cap3 - 1) / cap3) * 64.0, est2 = (double)((n_tasks + cap2 - 1) / cap2) * 42.0;
+            c->e_minb = est2 <= est3 ? 2 : 3;
+            if (const char *e = std::getenv("SIGNER_E_MINB")) { const int v = std::atoi(e); if (v == 2 || v == 3) c->e_minb = v; }   // experiments
+            per_sm = c->e_minb == 2 ? per2 : per3;
+        }
         const int want = c->I > kERows ? e_groups(c->J) : (n_tasks + c->e_warps - 1) / c->e_warps;   // chunked contexts: whole column groups per block
         c->e_grid = std::max(1, std::min(std::max(1, per_sm) * sms, want));   // one round per block where they all fit
     }
