@@ -52,7 +52,7 @@ struct Hyper { double ap, bp, ae, be, lp, le, var_ap, var_ae; };
 // integer atomics.  Batches are claimed heaviest-first from a global counter; a batch of small counts
 // claims its successor and fetches its list entries while it draws.
 // ------------------------------------------------------------------------------------------------
-constexpr int kZMaxWarps = 24;   // most warps per block; the host picks the block size per K (z_pick_block) -- the warps of a
+constexpr int kZMaxWarps = 24, kZFewWarps = 16;   // most warps per block (the two register budgets of the kernel); the host picks the block size per K (z_pick_block) -- the warps of a
                                  // block share only its Zin accumulator
 constexpr int kZChunk = 1;        // batches of 32 cells per claim
 constexpr int kNDirect = 32;      // largest count drawn by the direct method
@@ -215,7 +215,11 @@ SG_D void prefetch_tables(int t)
 
 SG_D int z_expo(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
-__global__ void __launch_bounds__(32 * kZMaxWarps, 1) z_alloc_fused(const ZParams p)
+// MAXW: most warps per SM the register budget is set for -- 24 (80 registers) or 16 (128 registers: the kernel as the
+// compiler wants it, 15 % faster per warp).  24 warps at 80 registers win by ~5 % where 24 fit; where shared memory holds
+// fewer (96 contexts from K = 28: 10 KB of cumulative sums per warp) the 128-register build does; chain_create picks.
+template <int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1) z_alloc_fused(const ZParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

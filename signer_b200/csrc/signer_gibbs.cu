@@ -58,9 +58,12 @@ int ensure_device_setup(int device)
     int optin = 0;
     CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, z_alloc_fused));
+    CU(cudaFuncGetAttributes(&fa, z_alloc_fused<kZMaxWarps>));
     g_z_dyn_smem_max[device] = optin - (int)fa.sharedSizeBytes;
-    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
+    CU(cudaFuncGetAttributes(&fa, z_alloc_fused<kZFewWarps>));
+    g_z_dyn_smem_max[device] = std::min(g_z_dyn_smem_max[device], optin - (int)fa.sharedSizeBytes);
+    CU(cudaFuncSetAttribute(z_alloc_fused<kZMaxWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
+    CU(cudaFuncSetAttribute(z_alloc_fused<kZFewWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_z_dyn_smem_max[device]));
     CU(cudaFuncGetAttributes(&fa, loglik_cols));          // 8 (129 K + 3264) bytes: above 48 KB from K = 23; 158 KB at K = 128, the largest accepted
     CU(cudaFuncSetAttribute(loglik_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     CU(cudaFuncGetAttributes(&fa, e_family<kEWarps, 3>));    // two W tiles: 51 KB
@@ -76,7 +79,7 @@ int ensure_device_setup(int device)
     CU(cudaFuncGetAttributes(&fa, seg_reduce));
     CU(cudaFuncSetAttribute(seg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
 #ifdef SG_Z_CARVEOUT
-    CU(cudaFuncSetAttribute(z_alloc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, SG_Z_CARVEOUT));
+    CU(cudaFuncSetAttribute(z_alloc_fused<kZMaxWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, SG_Z_CARVEOUT));
 #endif
     done[device] = true;
     return SIGNER_OK;
@@ -188,7 +191,7 @@ struct signer_chain {
     unsigned long long *tile_counter = nullptr;
     unsigned *ll_ticket = nullptr;               // block counter of loglik_cols' fused tree
     unsigned long long z_launches = 0;
-    int z_grid = 0, z_warps = 8, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
+    int z_grid = 0, z_warps = 8, z_budget = kZMaxWarps, n_batches = 0, n_chunks = 0, z_warp_smem = 0, z_zin_smem = 0;
     int e_grid = 1, e_warps = kEWarps, e_minb = 3, sms = 1;
     Hyper h{};
     Key key{};
@@ -302,7 +305,9 @@ int launch_z(signer_chain *c, uint32_t sweep, uint32_t stream_id, double *zcube)
     if (zcube) CU(cudaMemsetAsync(zcube, 0, sizeof(double) * (size_t)c->I * c->J * c->K, c->stream));
     {
         ProfScope ps(c, 0);
-        z_alloc_fused<<<c->z_grid, 32 * c->z_warps, (size_t)c->z_warp_smem * c->z_warps + (c->z_zin_smem ? c->nP * sizeof(int) : 0), c->stream>>>(p);
+        const size_t zsm = (size_t)c->z_warp_smem * c->z_warps + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
+        if (c->z_budget == kZFewWarps) z_alloc_fused<kZFewWarps><<<c->z_grid, 32 * c->z_warps, zsm, c->stream>>>(p);
+        else z_alloc_fused<kZMaxWarps><<<c->z_grid, 32 * c->z_warps, zsm, c->stream>>>(p);
     }
     ST(check_launch(c->stream, "z_alloc_fused"));
     c->z_launches++;
@@ -707,18 +712,42 @@ int chain_create(std::shared_ptr<DeviceData> data, int K, const signer_state *st
     // in shared memory, which leaves more of the SM's 256 KB to L1)
     int sms = 0, best_w = 0, best_b = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    for (int w : {24, 12, 8, 6, 4, 3, 2, 1}) {
-        const size_t zsm = (size_t)c->z_warp_smem * w + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
-        if (zsm > (size_t)g_z_dyn_smem_max[c->device]) continue;
-        int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused, 32 * w, zsm));
-        occ = std::min(occ, kZMaxWarps / w);
-        if (occ * w > best_w * best_b) { best_w = w; best_b = occ; }
+    // Block width and register budget: the candidate with the smallest estimated launch time.  Measured on configs 3 and 5
+    // over K = 5..40 (profiles/r02_measurements.md section 5): at 80 registers a launch takes 1 + 0.23 (24 - warps) / 8 of its
+    // time at 24 warps per SM; the 128-register build at 16 warps 1.046 of that; and what the cumulative sums leave of the SM's
+    // 256 KB for L1 matters to the 80-register build, whose spills (128 bytes x 768 threads) live there next to the gathers of E
+    // columns and of the work list -- the shared-memory carve-out steps are ..., 164, 196, 228 KB: 60 KB of L1 cost it ~7 %,
+    // 28 KB ~20 %; the 128-register build (48 bytes of stack) showed no such step up to K = 40.
+    auto l1_factor = [&](int w, int b) {
+        const size_t per_block = (size_t)c->z_warp_smem * w + (c->z_zin_smem ? c->nP * sizeof(int) : 0) + 2048;   // + static + reserved
+        const size_t kb = (per_block * (size_t)b + 1023) / 1024;
+        size_t carve = 228;
+        for (size_t step : {0, 8, 16, 32, 64, 100, 132, 164, 196, 228}) if (step >= kb) { carve = step; break; }
+        const size_t l1 = 256 - carve;
+        return l1 >= 92 ? 1.0 : l1 >= 60 ? 1.075 : 1.20;
+    };
+    int forced_budget = 0;
+    if (const char *e = std::getenv("SIGNER_Z_BUDGET")) forced_budget = std::atoi(e);       // experiments: force the register budget
+    double best_est = 1e30;
+    for (int budget : {kZMaxWarps, kZFewWarps}) {
+        if (forced_budget && budget != forced_budget) continue;
+        for (int w : {24, 16, 12, 8, 6, 4, 3, 2, 1}) {
+            if (w > budget) continue;
+            const size_t zsm = (size_t)c->z_warp_smem * w + (c->z_zin_smem ? c->nP * sizeof(int) : 0);
+            if (zsm > (size_t)g_z_dyn_smem_max[c->device]) continue;
+            int occ = 0;
+            if (budget == kZFewWarps) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused<kZFewWarps>, 32 * w, zsm));
+            else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, z_alloc_fused<kZMaxWarps>, 32 * w, zsm));
+            occ = std::min(occ, budget / w);
+            if (occ < 1) continue;
+            const double est = (1.0 + 0.23 * (budget - occ * w) / 8.0) * (budget == kZFewWarps ? 1.046 : l1_factor(w, occ));
+            if (est < best_est - 1e-9) { best_est = est; best_w = w; best_b = occ; c->z_budget = budget; }   // ties: fewer, larger blocks
+        }
     }
     if (best_w == 0) return fail(SIGNER_ERR_ARG, "z_alloc_fused: K too large for shared memory");
     if (const char *e = std::getenv("SIGNER_Z_BLOCK")) {          // experiments: "warps:blocks_per_sm"
         int w = 0, b = 0;
-        if (std::sscanf(e, "%d:%d", &w, &b) == 2 && w >= 1 && w <= kZMaxWarps && b >= 1) { best_w = w; best_b = b; }
+        if (std::sscanf(e, "%d:%d", &w, &b) == 2 && w >= 1 && w * b <= c->z_budget && b >= 1) { best_w = w; best_b = b; }
     }
     c->z_warps = best_w;
     c->z_grid = std::max(1, std::min((c->n_chunks + best_w - 1) / best_w, best_b * sms));
