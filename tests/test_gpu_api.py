@@ -111,3 +111,15 @@ def test_many_ring_chunks_are_bit_exact(sg, oracle, monkeypatch):
     monkeypatch.setenv("SIGNER_RING_BYTES", str(2 * 2 * slice_bytes))        # keep_par=FALSE: two slices per sweep
     got, want = run_both(sg, oracle, M, W, st, 6, burn=2, eval=13, keep_par=False, seed=2212)
     compare_all(got, want, keep_par=False)
+
+
+@pytest.mark.parametrize("e_minb,z_budget", [("2", "16"), ("3", "24"), ("2", "24"), ("3", "16")])
+def test_register_budgets_give_identical_results(sg, oracle, monkeypatch, e_minb, z_budget):
+    """z_alloc_fused and e_family exist with two register budgets each (chain_create picks by shape): the same code under a
+    different register allocation, so every output must still equal the oracle bit for bit whichever build is forced"""
+    M, W, st = small_problem(I=96, J=700, K=9, seed=12, burden=3000.0)
+    M[3, 5] = 5000.0
+    monkeypatch.setenv("SIGNER_E_MINB", e_minb)
+    monkeypatch.setenv("SIGNER_Z_BUDGET", z_budget)
+    got, want = run_both(sg, oracle, M, W, st, 9, burn=4, eval=3, keep_par=True, seed=3300 + int(e_minb) + int(z_budget))
+    compare_all(got, want)
