@@ -40,7 +40,8 @@ namespace {
 thread_local double g_loop_ms = 0.0;      // wall time of the last sweep loop on this thread (sharded / stateless runs)
 
 constexpr int kMaxRingSets = 8;                     // short runs: one set per chunk, the host never waits for a set to drain
-constexpr size_t kRingBytes = size_t(64) << 20;    // per ring set (two sets): what is still on the device when the last sweep ends is the call's tail
+constexpr size_t kRingBytes = size_t(64) << 20;    // per ring set: what is still on the device when the last sweep ends is the call's tail
+constexpr size_t kRingTotalBytes = size_t(512) << 20;   // all ring sets of a chain: how far the sweeps may run ahead of the copy-out
 
 // z_alloc_fused and loglik_cols may need more than 48 KB of dynamic shared memory; raise the limits once per device to
 // the architectural maximum so that concurrent chains with different K never race on the attribute.
@@ -485,12 +486,16 @@ int ring_chunk(const signer_chain *c, int eval, int keep_par)
     return (int)std::max<size_t>(1, std::min<size_t>(fit, ((size_t)eval + 7) / 8));
 }
 
-// Ring sets: two of up to kRingBytes each, or more (smaller) ones within the same memory when the chunks are short
+// Ring sets: as many as kRingTotalBytes hold (two at least, kMaxRingSets at most, never more than the run has chunks).  With
+// keep_par a config-3 sweep leaves 4.8 MB of samples, 24 GB/s at 0.2 ms per sweep -- about what the copy-out path sustains into
+// fresh pageable memory -- so the EM loop's call runs ahead of its copy-out most of the time; with two sets its enqueue waited
+// for drains and the device idled (measured: 100 - 107 ms per call against 91 with eight)
 int ring_set_count(const signer_chain *c, int eval, int keep_par)
 {
     const size_t per_sweep = sizeof(double) * (c->nP + c->nE) * (keep_par ? 3 : 2);
     const int cap = ring_chunk(c, eval, keep_par), chunks = (eval + cap - 1) / cap;
-    const size_t fit = (2 * ring_bytes_limit()) / std::max<size_t>(1, per_sweep * (size_t)cap);
+    const size_t total = std::getenv("SIGNER_RING_BYTES") ? 2 * ring_bytes_limit() : kRingTotalBytes;   // (tests: two small sets, reused many times)
+    const size_t fit = total / std::max<size_t>(1, per_sweep * (size_t)cap);
     return (int)std::max<size_t>(2, std::min<size_t>({(size_t)kMaxRingSets, fit, (size_t)chunks}));
 }
 
